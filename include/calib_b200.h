@@ -1,0 +1,170 @@
+/* calib_b200.h - C ABI of the B200-native calibration hot path.
+ *
+ * Drop-in boundary for the per-frame calibration path of
+ * NikolasEnt/soccernet-calibration-sportlight.  The reference is pure Python with
+ * no FFI of its own: its plug-in points are Python classes
+ * selected by Hydra `_target_` strings.  The Python package in
+ * soccernet_calibration_sportlight_b200/ mirrors those classes and binds the entry
+ * points below with ctypes.  Each entry point cites the
+ * reference interface it replaces as `file:line` under /root/reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name starts with `h_` (host);
+ *   - the caller owns every buffer; nothing is allocated behind the ABI;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     all work is enqueued asynchronously on it, no host synchronisation;
+ *   - return value: 0 = CAL_OK, negative = CalStatus; cal_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns CAL_E_CUDA.
+ */
+#ifndef CALIB_B200_H_
+#define CALIB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAL_ABI_VERSION 1
+
+typedef enum CalStatus {
+  CAL_OK = 0,
+  CAL_E_INVALID = -1,     /* bad argument (shape, alignment, null pointer) */
+  CAL_E_UNSUPPORTED = -2, /* shape outside what the kernels were built for */
+  CAL_E_CUDA = -3,        /* CUDA runtime / driver error (message has details) */
+} CalStatus;
+
+int cal_abi_version(void);
+const char* cal_last_error(void);
+
+/* ------------------------------------------------------------------ decode -- */
+
+/* Keypoint heat-map decode.
+ * Replaces HRNetPredictionTransform.__call__ (src/models/hrnet/transforms.py:228-239).
+ *   logp : (B, C, h, w) fp32 log-probabilities, contiguous NCHW
+ *   out  : (B, C-1, 3) fp32 [x, y, conf]; the last channel (background) is dropped
+ *   x = first argmax over columns of the column maxima of exp(logp), scaled by
+ *   W_img / w ; y likewise over rows, scaled by H_img / h ; conf = min of the two
+ *   maxima.  exp is the correctly rounded fp32 exponential; ties -> first index. */
+int cal_kp_decode(const float* logp, int B, int C, int h, int w, int H_img, int W_img,
+                  float* out, void* stream);
+
+/* Line heat-map decode (two peaks per channel with Gaussian suppression).
+ * Replaces EHMPredictionTransform.mask_heat_points_gauss and __call__
+ * (src/models/line/transforms.py:216-280).
+ *   heat : (B, C, h, w) fp32 probabilities
+ *   out  : (B, C, 2, 3) fp32 [x*scale, y*scale, value] for peak 1 and peak 2
+ *   scale = 1 reproduces mask_heat_points_gauss; __call__ uses its `scale`. */
+int cal_line_decode(const float* heat, int B, int C, int h, int w, double sigma, float scale,
+                    float* out, void* stream);
+
+/* ------------------------------------------------------- HRNet building ops -- */
+/* Activations are fp16 NHWC with the channel count padded to a multiple of 64
+ * (zero-filled pad lanes); accumulation is fp32 on tcgen05 tensor cores.  These
+ * ops together replace HighResolutionNet.forward (src/models/hrnet/hrnet.py:437-511,
+ * src/models/line/hrnet.py:185-249); the layer schedule itself lives in the Python
+ * mirror (hrnet.py in the package), one call per fused conv+BN(+add)(+ReLU). */
+
+typedef struct CalConvArgs {
+  const void* x;     /* fp16 NHWC (B, Hin, Win, Cin_pad) */
+  const void* w;     /* fp16 (Cout_rows, taps, Cin_pad), BN folded, K-major */
+  const float* bias; /* fp32 (Cout_pad), BN folded; pad lanes zero */
+  const void* res;   /* optional fp16 NHWC (B, Hout, Wout, Cout_pad) added before ReLU */
+  void* y;           /* mode 0: fp16 NHWC (B, Hout, Wout, Cout_pad);
+                        mode 1/2: fp32 NCHW (B, n_classes, Hout, Wout) */
+  int32_t B, Hin, Win, Cin_pad;
+  int32_t Hout, Wout, Cout_pad;
+  int32_t Cout_rows; /* rows in w: real Cout rounded up to 16 */
+  int32_t ksize;     /* 1 or 3 (padding = ksize/2) */
+  int32_t stride;    /* 1 or 2 */
+  int32_t relu;      /* mode 0 only */
+  int32_t mode;      /* 0 = fp16 NHWC; 1 = LogSoftmax over n_classes -> fp32 NCHW
+                        (hrnet.py:329); 2 = Softmax (line/hrnet.py:101) */
+  int32_t n_classes; /* modes 1/2: 58 / 23 */
+} CalConvArgs;
+
+/* conv (+folded BN) (+residual) (+ReLU) as an implicit GEMM on tcgen05/TMEM with
+ * TMA-staged operands.  Replaces nn.Conv2d + BatchNorm2d + add + ReLU groups
+ * (hrnet.py:42-58, 79-99, 184-213, 260-266, 316-330, 366-388). */
+int cal_conv2d(const CalConvArgs* h_args, void* stream);
+
+/* Stem conv1: 3x3 stride-2 conv 3->64 + BN + ReLU straight from the fp32 NCHW
+ * frame tensor (hrnet.py:450-452).  x: (B,3,H,W) fp32 in [0,1] BGR;
+ * w: fp32 (64, 27) BN folded [co][ci*9+ky*3+kx]; y: fp16 NHWC (B,Ho,Wo,64). */
+int cal_stem_conv(const float* x, const float* w, const float* bias, void* y,
+                  int B, int H, int W, int Ho, int Wo, void* stream);
+
+#define CAL_MAX_SOURCES 6
+typedef struct CalCombineArgs {
+  void* y;        /* fp16 NHWC (B, H, W, C_pad) */
+  int32_t B, H, W, C_pad;
+  int32_t n_src;
+  const void* src[CAL_MAX_SOURCES]; /* fp16 NHWC (B, h_i, w_i, C_pad) */
+  int32_t src_h[CAL_MAX_SOURCES];   /* == H,W: plain add; else bilinear, align_corners=True */
+  int32_t src_w[CAL_MAX_SOURCES];
+  const float* bias;                /* optional fp32 (C_pad) */
+  int32_t relu;
+} CalCombineArgs;
+
+/* y = [relu]( bias + sum_i up_i(src_i) ): the multi-resolution fuse of
+ * HighResolutionModule.forward (hrnet.py:229-246) and the head's upsample+concat
+ * (hrnet.py:489-509, line/hrnet.py:236-245) after commuting the 1x1 conv with the
+ * bilinear interpolation. */
+int cal_fuse_combine(const CalCombineArgs* h_args, void* stream);
+
+/* ------------------------------------------------------------ camera solve -- */
+
+typedef struct CalSolveParams {
+  int32_t algorithm;  /* 0 opencv_calibration, 1 opencv_calibration_multiplane,
+                         2 original_voter, 3 voter, 4 iterative_voter
+                         (src/models/hrnet/prediction.py:90-96) */
+  int32_t img_w, img_h;
+  float conf_thresh;
+  float conf_threshs[8];
+  int32_t n_conf_threshs;
+  int32_t min_points, min_points_per_plane, min_points_for_refinement, reliable_thresh;
+  float min_focal_length, max_rmse, max_rmse_rel;
+} CalSolveParams;
+
+typedef struct CalCameraRecord { /* 128 bytes, the all-gather payload */
+  double position[3];
+  double rotation[9]; /* row-major world->camera */
+  double fx, fy;
+  double rmse;        /* mean reprojection L2 of the selected camera (Camera.projection_rmse) */
+  int32_t valid;      /* 0 = reference would return None */
+  int32_t branch;     /* which heuristic produced it (diagnostics) */
+} CalCameraRecord;
+
+/* Batched CameraCreator.__call__ (src/models/hrnet/prediction.py:130-136 and the
+ * algorithms it dispatches to, :138-437, with baseline/camera.py:92-119, 366-426):
+ * one thread block per frame.
+ *   preds    : (B, 57, 3) fp32 [x, y, conf]
+ *   line_pts : optional (B, 57, 2) fp64 keypoints from line intersections, NaN = absent
+ *   out      : (B) records */
+int cal_camera_solve(const float* preds, const double* line_pts, const CalSolveParams* h_params,
+                     int B, CalCameraRecord* out, void* stream);
+
+/* Single-camera helpers used by the Camera class mirror.
+ * cal_pnp_refine  replaces Camera.refine_camera (baseline/camera.py:105-119);
+ * cal_pnp_solve   replaces Camera.solve_pnp     (baseline/camera.py:92-103).
+ *   obj (n,3) fp64, img (n,2) fp64, K (9) fp64 row-major, rvec/tvec (3) fp64 in/out */
+int cal_pnp_refine(const double* obj, const double* img, int n, const double* K,
+                   double* rvec, double* tvec, void* stream);
+int cal_pnp_solve(const double* obj, const double* img, int n, const double* K,
+                  double* rvec, double* tvec, int32_t* ok, void* stream);
+
+/* ------------------------------------------------------------------- debug -- */
+/* Dumps the shared-memory image of one TMA box load (used by tests to pin the
+ * tensor-map conventions the conv kernel relies on). */
+int cal_debug_tma_probe(const void* x, int B, int H, int W, int C, int box_w, int box_h,
+                        int estride, int c0, int x0, int y0, int n0, void* out_smem_16k,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CALIB_B200_H_ */

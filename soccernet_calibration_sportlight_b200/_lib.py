@@ -1,0 +1,94 @@
+"""ctypes binding of the C-ABI library (include/calib_b200.h).  There is no CPU
+fallback: if the shared library is missing the import fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcalib_b200.so")
+
+CAL_MAX_SOURCES = 6
+
+EXPORTS = [
+    "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
+    "cal_stem_conv", "cal_fuse_combine", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
+    "cal_debug_tma_probe",
+]
+
+
+class CalError(RuntimeError):
+    pass
+
+
+class ConvArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p), ("res", C.c_void_p),
+                ("y", C.c_void_p),
+                ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin_pad", C.c_int32),
+                ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout_pad", C.c_int32),
+                ("Cout_rows", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
+                ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32)]
+
+
+class CombineArgs(C.Structure):
+    _fields_ = [("y", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C_pad", C.c_int32),
+                ("n_src", C.c_int32),
+                ("src", C.c_void_p * CAL_MAX_SOURCES),
+                ("src_h", C.c_int32 * CAL_MAX_SOURCES),
+                ("src_w", C.c_int32 * CAL_MAX_SOURCES),
+                ("bias", C.c_void_p), ("relu", C.c_int32)]
+
+
+class SolveParams(C.Structure):
+    _fields_ = [("algorithm", C.c_int32), ("img_w", C.c_int32), ("img_h", C.c_int32),
+                ("conf_thresh", C.c_float), ("conf_threshs", C.c_float * 8),
+                ("n_conf_threshs", C.c_int32),
+                ("min_points", C.c_int32), ("min_points_per_plane", C.c_int32),
+                ("min_points_for_refinement", C.c_int32), ("reliable_thresh", C.c_int32),
+                ("min_focal_length", C.c_float), ("max_rmse", C.c_float), ("max_rmse_rel", C.c_float)]
+
+
+class CameraRecord(C.Structure):
+    _fields_ = [("position", C.c_double * 3), ("rotation", C.c_double * 9),
+                ("fx", C.c_double), ("fy", C.c_double), ("rmse", C.c_double),
+                ("valid", C.c_int32), ("branch", C.c_int32)]
+
+
+assert C.sizeof(CameraRecord) == 128
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and type the library.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CalError(f"{LIB_PATH} not built: run `python __graft_entry__.py` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, f32, f64 = C.c_void_p, C.c_int, C.c_float, C.c_double
+    L.cal_abi_version.restype = C.c_int
+    L.cal_last_error.restype = C.c_char_p
+    L.cal_kp_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.cal_line_decode.argtypes = [vp, i32, i32, i32, i32, f64, f32, vp, vp]
+    L.cal_conv2d.argtypes = [C.POINTER(ConvArgs), vp]
+    L.cal_stem_conv.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]
+    L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    if hasattr(L, "cal_camera_solve"):
+        L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
+        L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+        L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    for name in EXPORTS:
+        if hasattr(L, name) and name != "cal_last_error":
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = lib().cal_last_error().decode("utf-8", "replace")
+        raise CalError(f"{what} failed with status {status}: {msg}")

@@ -1,0 +1,390 @@
+// conv_tc.cu - convolution (+folded BN)(+residual)(+ReLU / (Log)Softmax) as an
+// implicit GEMM on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA.  Replaces the Conv2d+BatchNorm2d(+add)+ReLU groups of
+// src/models/hrnet/hrnet.py:42-58, 79-99, 184-213, 260-266, 316-330, 366-388.
+//
+// GEMM view: D[M=128 pixels][N=Cout] += A[M][K] * W[N][K]^T with K = taps * Cin_pad.
+//   * One CTA tile = a TH x TW rectangle of output pixels of one frame (TH*TW <= 128)
+//     times up to 256 output channels.
+//   * A operand: for every filter tap the (Cin chunk of 64) x TW x TH box of the
+//     NHWC fp16 activation tensor is fetched by ONE 4-D TMA load whose start
+//     coordinate is shifted by the tap offset; out-of-image elements are zero-filled
+//     by the TMA unit (the conv padding), stride-2 convs use the tensor map's
+//     element strides.  Rows land as 128-byte SWIZZLE_128B lines = the canonical
+//     K-major UMMA layout, so the box IS the MMA operand (no im2col buffer).
+//   * B operand: (64 K-elements) x N box of the packed weights [Cout][tap][Cin].
+//   * Persistent CTAs (one per SM), static round-robin tile schedule, 3 roles:
+//     warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+//     warps 2..9 = epilogue (TMEM -> registers -> bias/residual/ReLU -> fp16 NHWC),
+//     mbarrier ring between producer and MMA, double-buffered TMEM accumulators
+//     between MMA and epilogue so tile i+1's MMAs overlap tile i's epilogue.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int CONV_THREADS = 320;          // 10 warps
+constexpr int A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 fp16
+constexpr int KC = 64;                     // K elements per pipeline stage
+constexpr int MAX_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+constexpr int ACC_STRIDE = 256;            // TMEM column offset of accumulator stage 1
+constexpr int MAX_BIAS = 1024;
+
+struct ConvParams {
+  int B, Hout, Wout, Cout_pad;
+  int TW, TH, tiles_x, tiles_y, n_tiles, total_tiles;
+  int N_tile;        // output-channel span of one tile in the padded channel space
+  int mma_n;         // N of the MMA instruction (<= N_tile, multiple of 16)
+  int kc_per_tap, taps, stride, pad, num_k;
+  int relu, mode, n_classes;
+  int stages, b_stage_bytes;
+  uint32_t tx_bytes;
+  const float* bias;
+  const __half* res;
+  void* y;
+};
+
+struct TileCoord { int n0, b, y0, x0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int t) {
+  TileCoord c;
+  const int nt = t % p.n_tiles;
+  int mt = t / p.n_tiles;
+  c.n0 = nt * p.N_tile;
+  const int txi = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int tyi = mt % p.tiles_y;
+  c.b = mt / p.tiles_y;
+  c.y0 = tyi * p.TH;
+  c.x0 = txi * p.TW;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const ConvParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A stages][B stages][barriers][tmem slot][bias]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + p.stages * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + p.stages * p.b_stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + MAX_STAGES;
+  uint64_t* tfull = bars + 2 * MAX_STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < p.Cout_pad; i += CONV_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t);
+        const int xs = tc.x0 * p.stride - p.pad, ys = tc.y0 * p.stride - p.pad;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (p.taps == 9) ? tap / 3 : 0, dx = (p.taps == 9) ? tap - 3 * dy : 0;
+          for (int cc = 0; cc < p.kc_per_tap; ++cc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], p.tx_bytes);
+            tma_load_4d(sA + stage * A_STAGE_BYTES, &tmA, &full[stage], cc * KC, xs + dx, ys + dy, tc.b);
+            tma_load_2d(sB + stage * p.b_stage_bytes, &tmB, &full[stage],
+                        (tap * p.kc_per_tap + cc) * KC, tc.n0);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+        for (int k = 0; k < p.num_k; ++k) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 128, 2);
+          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * p.b_stage_bytes), 128, 2);
+#pragma unroll
+          for (int kk = 0; kk < KC / 16; ++kk) {
+            // +32 bytes per K=16 step inside the 128-byte swizzle span
+            umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull[as]);        // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // which half of the column groups
+    const int groups_total = p.N_tile >> 4;
+    const int groups_mma = p.mma_n >> 4;
+    const int g_split = (groups_total + 1) >> 1;
+    const int g_begin = (p.mode == 0) ? (half ? g_split : 0) : 0;
+    const int g_end = (p.mode == 0) ? (half ? groups_total : g_split) : (half ? 0 : groups_total);
+    const int m = quarter * 32 + lane;
+    const int ty = m / p.TW, tx = m - ty * p.TW;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(p, t);
+      const int y = tc.y0 + ty, x = tc.x0 + tx;
+      const bool valid = (m < p.TW * p.TH) && (y < p.Hout) && (x < p.Wout);
+      const size_t pix = (static_cast<size_t>(tc.b) * p.Hout + y) * p.Wout + x;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (p.mode == 0) {
+        __half* yrow = reinterpret_cast<__half*>(p.y) + pix * p.Cout_pad + tc.n0;
+        const __half* rrow = p.res ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
+        for (int g = g_begin; g < g_end; ++g) {
+          uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0;
+          if (rrow && valid) {
+            rq0 = __ldg(reinterpret_cast<const uint4*>(rrow + g * 16));
+            rq1 = __ldg(reinterpret_cast<const uint4*>(rrow + g * 16 + 8));
+          }
+          float v[16];
+          if (g < groups_mma) {
+            uint32_t r[16];
+            tmem_ld16(taddr + g * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+          }
+          if (valid) {
+            const float* bb = s_bias + tc.n0 + g * 16;
+            const uint32_t rr[8] = {rq0.x, rq0.y, rq0.z, rq0.w, rq1.x, rq1.y, rq1.z, rq1.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+              float a = v[2 * j] + bb[2 * j] + __low2float(rh);
+              float b = v[2 * j + 1] + bb[2 * j + 1] + __high2float(rh);
+              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+              o[j] = pack_half2(a, b);
+            }
+            *reinterpret_cast<uint4*>(yrow + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(yrow + g * 16 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      } else if (half == 0) {
+        // (Log)Softmax over the first n_classes columns of this pixel row, fp32 NCHW out
+        float v[64];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (g < groups_mma) {
+            uint32_t r[16];
+            tmem_ld16(taddr + g * 16, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[g * 16 + j] = __uint_as_float(r[j]) + s_bias[g * 16 + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[g * 16 + j] = 0.0f;
+          }
+        }
+        if (valid) {
+          float mx = -CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) if (j < p.n_classes) mx = fmaxf(mx, v[j]);
+          float sum = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) if (j < p.n_classes) sum += expf(v[j] - mx);
+          const float lse = logf(sum), inv = 1.0f / sum;
+          float* out = reinterpret_cast<float*>(p.y);
+          const size_t plane = static_cast<size_t>(p.Hout) * p.Wout;
+          const size_t base = static_cast<size_t>(tc.b) * p.n_classes * plane + static_cast<size_t>(y) * p.Wout + x;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            if (j < p.n_classes) {
+              const float d = v[j] - mx;
+              out[base + j * plane] = (p.mode == 1) ? (d - lse) : (expf(d) * inv);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// smem image of one TMA box, for pinning the tensor-map conventions in tests
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int x0, int y0,
+                                 int n0, uint32_t bytes, uint4* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu, 0xDEADBEEFu);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, bytes);
+    tma_load_4d(smem, &tm, &bar, c0, x0, y0, n0);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += blockDim.x) out[i] = reinterpret_cast<uint4*>(smem)[i];
+}
+
+int make_act_tmap(CUtensorMap* tm, const void* x, int B, int H, int W, int C, int box_w, int box_h,
+                  int estride) {
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint32_t box[4] = {(uint32_t)KC, (uint32_t)box_w, (uint32_t)box_h, 1};
+  const uint32_t es[4] = {1, (uint32_t)estride, (uint32_t)estride, 1};
+  return encode_tmap_f16(tm, x, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace
+}  // namespace cal
+
+extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(a != nullptr, CAL_E_INVALID, "cal_conv2d: null args");
+  CAL_REQUIRE(a->x && a->w && a->y, CAL_E_INVALID, "cal_conv2d: null tensor pointer");
+  CAL_REQUIRE(a->ksize == 1 || a->ksize == 3, CAL_E_UNSUPPORTED, "cal_conv2d: ksize %d", a->ksize);
+  CAL_REQUIRE(a->stride == 1 || a->stride == 2, CAL_E_UNSUPPORTED, "cal_conv2d: stride %d", a->stride);
+  CAL_REQUIRE(a->B >= 1 && a->Hin >= 1 && a->Win >= 1 && a->Hout >= 1 && a->Wout >= 1, CAL_E_INVALID,
+              "cal_conv2d: bad spatial shape");
+  CAL_REQUIRE(a->Cin_pad % KC == 0 && a->Cin_pad >= KC, CAL_E_INVALID, "cal_conv2d: Cin_pad %d not a multiple of 64", a->Cin_pad);
+  CAL_REQUIRE(a->Cout_pad % 64 == 0 && a->Cout_pad >= 64 && a->Cout_pad <= MAX_BIAS, CAL_E_INVALID,
+              "cal_conv2d: Cout_pad %d", a->Cout_pad);
+  CAL_REQUIRE(a->Cout_rows % 16 == 0 && a->Cout_rows >= 16 && a->Cout_rows <= a->Cout_pad, CAL_E_INVALID,
+              "cal_conv2d: Cout_rows %d", a->Cout_rows);
+  const int pad = a->ksize / 2;
+  CAL_REQUIRE(a->Hout == (a->Hin + 2 * pad - a->ksize) / a->stride + 1 &&
+                  a->Wout == (a->Win + 2 * pad - a->ksize) / a->stride + 1,
+              CAL_E_INVALID, "cal_conv2d: output size %dx%d inconsistent with input %dx%d k%d s%d", a->Hout,
+              a->Wout, a->Hin, a->Win, a->ksize, a->stride);
+  CAL_REQUIRE(a->mode >= 0 && a->mode <= 2, CAL_E_INVALID, "cal_conv2d: mode %d", a->mode);
+  if (a->mode != 0)
+    CAL_REQUIRE(a->Cout_pad == 64 && a->n_classes >= 1 && a->n_classes <= a->Cout_rows && !a->res, CAL_E_UNSUPPORTED,
+                "cal_conv2d: softmax modes need Cout_pad == 64, n_classes <= Cout_rows, no residual");
+
+  ConvParams p{};
+  p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout; p.Cout_pad = a->Cout_pad;
+  // tile rectangle: minimise the tile count, prefer wide tiles
+  int best_tw = 1, best_th = 1;
+  long best = -1;
+  for (int tw = 1; tw <= 128 && tw <= a->Wout; ++tw) {
+    int th = 128 / tw;
+    if (th > a->Hout) th = a->Hout;
+    if (th < 1) continue;
+    const long tiles = (long)((a->Wout + tw - 1) / tw) * ((a->Hout + th - 1) / th);
+    if (best < 0 || tiles < best || (tiles == best && tw > best_tw)) { best = tiles; best_tw = tw; best_th = th; }
+  }
+  p.TW = best_tw; p.TH = best_th;
+  p.tiles_x = (a->Wout + p.TW - 1) / p.TW;
+  p.tiles_y = (a->Hout + p.TH - 1) / p.TH;
+  // channel tiling in the padded space
+  int n_tiles = 1;
+  while (a->Cout_pad % (16 * n_tiles) != 0 || a->Cout_pad / n_tiles > 256) ++n_tiles;
+  p.n_tiles = n_tiles;
+  p.N_tile = a->Cout_pad / n_tiles;
+  p.mma_n = p.N_tile < a->Cout_rows ? p.N_tile : a->Cout_rows;
+  p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
+  p.kc_per_tap = a->Cin_pad / KC;
+  p.taps = a->ksize * a->ksize;
+  p.stride = a->stride; p.pad = pad;
+  p.num_k = p.taps * p.kc_per_tap;
+  p.relu = a->relu; p.mode = a->mode; p.n_classes = a->n_classes;
+  p.bias = a->bias; p.res = reinterpret_cast<const __half*>(a->res); p.y = a->y;
+  p.b_stage_bytes = ((p.mma_n * 128) + 1023) & ~1023;
+  const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
+  const int tail_bytes = (2 * MAX_STAGES + 4) * 8 + 16 + MAX_BIAS * 4;
+  int stages = (200 * 1024 - tail_bytes) / stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  CAL_REQUIRE(stages >= 2, CAL_E_UNSUPPORTED, "cal_conv2d: tile does not fit shared memory");
+  p.stages = stages;
+  p.tx_bytes = (uint32_t)(p.TW * p.TH * 128 + p.mma_n * 128);
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_tmap(&tmA, a->x, a->B, a->Hin, a->Win, a->Cin_pad, p.TW * a->stride, p.TH * a->stride, a->stride);
+  if (rc != CAL_OK) return rc;
+  {
+    const uint64_t ktot = (uint64_t)p.taps * a->Cin_pad;
+    const uint64_t dims[2] = {ktot, (uint64_t)a->Cout_rows};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t box[2] = {(uint32_t)KC, (uint32_t)p.mma_n};
+    rc = encode_tmap_f16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != CAL_OK) return rc;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CAL_CHECK_CUDA(cudaGetDevice(&dev));
+    CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_tc_kernel<<<grid, CONV_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_debug_tma_probe(const void* x, int B, int H, int W, int C, int box_w, int box_h,
+                                   int estride, int c0, int x0, int y0, int n0, void* out_smem_16k,
+                                   void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(x && out_smem_16k, CAL_E_INVALID, "cal_debug_tma_probe: null pointer");
+  CAL_REQUIRE(C % 64 == 0 && estride >= 1 && estride <= 2, CAL_E_INVALID, "cal_debug_tma_probe: bad args");
+  const int nx = (box_w + estride - 1) / estride, ny = (box_h + estride - 1) / estride;
+  CAL_REQUIRE(nx * ny <= 128 && nx >= 1 && ny >= 1, CAL_E_INVALID, "cal_debug_tma_probe: box too large");
+  CUtensorMap tm;
+  int rc = make_act_tmap(&tm, x, B, H, W, C, box_w, box_h, estride);
+  if (rc != CAL_OK) return rc;
+  CAL_CHECK_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
+  tma_probe_kernel<<<1, 128, A_STAGE_BYTES + 1024, static_cast<cudaStream_t>(stream)>>>(
+      tm, c0, x0, y0, n0, (uint32_t)(nx * ny * 128), reinterpret_cast<uint4*>(out_smem_16k));
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}

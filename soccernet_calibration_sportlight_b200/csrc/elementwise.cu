@@ -1,0 +1,203 @@
+// elementwise.cu - the non-GEMM pieces of the HRNet forward.
+//
+//  cal_stem_conv    : first 3x3/s2 conv 3->64 (+BN+ReLU) straight from the fp32 NCHW
+//                     frame (src/models/hrnet/hrnet.py:450-452).  Cin = 3 gives K = 27,
+//                     too thin for the tensor cores: CUDA-core direct conv, one output
+//                     pixel per thread, weights broadcast from shared memory.
+//  cal_fuse_combine : y = [relu](bias + sum_i up_i(src_i)) over fp16 NHWC tensors, the
+//                     multi-resolution exchange of HighResolutionModule.forward
+//                     (hrnet.py:229-246) and the head's upsample (hrnet.py:489-509);
+//                     bilinear, align_corners=True, coordinates as in
+//                     torch.nn.functional.interpolate.  HBM-bound, 128-bit accesses.
+#include "common.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int STEM_CO = 64;
+constexpr int STEM_K = 27;
+
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x,
+                                                        const float* __restrict__ w,
+                                                        const float* __restrict__ bias,
+                                                        __half* __restrict__ y, int B, int H, int W,
+                                                        int Ho, int Wo) {
+  __shared__ __align__(16) float s_w[STEM_K * STEM_CO];   // [k][co]
+  __shared__ __align__(16) float s_b[STEM_CO];
+  for (int i = threadIdx.x; i < STEM_K * STEM_CO; i += blockDim.x) {
+    const int k = i / STEM_CO, co = i - k * STEM_CO;
+    s_w[i] = w[co * STEM_K + k];
+  }
+  for (int i = threadIdx.x; i < STEM_CO; i += blockDim.x) s_b[i] = bias[i];
+  __syncthreads();
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int ox = static_cast<int>(pix % Wo);
+  const int oy = static_cast<int>((pix / Wo) % Ho);
+  const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  float in[STEM_K];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+    const float* plane = x + (static_cast<size_t>(b) * 3 + ci) * H * W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy + ky - 1;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox + kx - 1;
+        const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
+        in[ci * 9 + ky * 3 + kx] = ok ? __ldg(plane + static_cast<size_t>(iy) * W + ix) : 0.0f;
+      }
+    }
+  }
+  __half* out = y + static_cast<size_t>(pix) * STEM_CO;
+#pragma unroll
+  for (int c0 = 0; c0 < STEM_CO; c0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = s_b[c0 + j];
+#pragma unroll
+    for (int k = 0; k < STEM_K; ++k) {
+      const float4* wr = reinterpret_cast<const float4*>(s_w + k * STEM_CO + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 ww = wr[q];
+        acc[4 * q + 0] = fmaf(in[k], ww.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(in[k], ww.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(in[k], ww.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(in[k], ww.w, acc[4 * q + 3]);
+      }
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      __half2 h = __floats2half2_rn(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(out + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(out + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+struct CombineParams {
+  __half* y;
+  int B, H, W, C8;       // C8 = C_pad / 8 (uint4 lanes per pixel)
+  int n_src;
+  const __half* src[CAL_MAX_SOURCES];
+  int sh[CAL_MAX_SOURCES], sw[CAL_MAX_SOURCES];
+  float scale_y[CAL_MAX_SOURCES], scale_x[CAL_MAX_SOURCES];
+  const float* bias;
+  int relu;
+};
+
+__device__ __forceinline__ void acc8(float* a, const uint4 q, float wgt) {
+  const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[j]));
+    a[2 * j] = fmaf(wgt, f.x, a[2 * j]);
+    a[2 * j + 1] = fmaf(wgt, f.y, a[2 * j + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(256) fuse_combine_kernel(const CombineParams p) {
+  const long long total = static_cast<long long>(p.B) * p.H * p.W * p.C8;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(idx % p.C8);
+    long long pix = idx / p.C8;
+    const int x = static_cast<int>(pix % p.W);
+    pix /= p.W;
+    const int y = static_cast<int>(pix % p.H);
+    const int b = static_cast<int>(pix / p.H);
+    float a[8];
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * c8);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * c8 + 1);
+      a[0] = b0.x; a[1] = b0.y; a[2] = b0.z; a[3] = b0.w;
+      a[4] = b1.x; a[5] = b1.y; a[6] = b1.z; a[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = 0.0f;
+    }
+#pragma unroll
+    for (int s = 0; s < CAL_MAX_SOURCES; ++s) {
+      if (s >= p.n_src) break;
+      const int sh = p.sh[s], sw = p.sw[s];
+      const uint4* base = reinterpret_cast<const uint4*>(p.src[s]) + static_cast<size_t>(b) * sh * sw * p.C8 + c8;
+      if (sh == p.H && sw == p.W) {
+        acc8(a, __ldg(base + (static_cast<size_t>(y) * sw + x) * p.C8), 1.0f);
+      } else {
+        // align_corners=True source coordinates (ATen area_pixel_compute_source_index)
+        const float fy = p.scale_y[s] * static_cast<float>(y);
+        const float fx = p.scale_x[s] * static_cast<float>(x);
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < sh - 1 ? 1 : 0), x1 = x0 + (x0 < sw - 1 ? 1 : 0);
+        const float ly1 = fy - static_cast<float>(y0), lx1 = fx - static_cast<float>(x0);
+        const float ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+        acc8(a, __ldg(base + (static_cast<size_t>(y0) * sw + x0) * p.C8), ly0 * lx0);
+        acc8(a, __ldg(base + (static_cast<size_t>(y0) * sw + x1) * p.C8), ly0 * lx1);
+        acc8(a, __ldg(base + (static_cast<size_t>(y1) * sw + x0) * p.C8), ly1 * lx0);
+        acc8(a, __ldg(base + (static_cast<size_t>(y1) * sw + x1) * p.C8), ly1 * lx1);
+      }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float u = a[2 * j], v = a[2 * j + 1];
+      if (p.relu) { u = fmaxf(u, 0.0f); v = fmaxf(v, 0.0f); }
+      __half2 h = __floats2half2_rn(u, v);
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    reinterpret_cast<uint4*>(p.y)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace
+}  // namespace cal
+
+extern "C" int cal_stem_conv(const float* x, const float* w, const float* bias, void* y, int B,
+                             int H, int W, int Ho, int Wo, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(x && w && bias && y, CAL_E_INVALID, "cal_stem_conv: null pointer");
+  CAL_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, CAL_E_INVALID,
+              "cal_stem_conv: bad shape %dx%d -> %dx%d", H, W, Ho, Wo);
+  const long long total = static_cast<long long>(B) * Ho * Wo;
+  const int threads = 128;
+  const long long blocks = (total + threads - 1) / threads;
+  CAL_REQUIRE(blocks < (1ll << 31), CAL_E_UNSUPPORTED, "cal_stem_conv: too many pixels");
+  stem_conv_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, w, bias, reinterpret_cast<__half*>(y), B, H, W, Ho, Wo);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_fuse_combine(const CalCombineArgs* a, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(a && a->y, CAL_E_INVALID, "cal_fuse_combine: null args");
+  CAL_REQUIRE(a->n_src >= 1 && a->n_src <= CAL_MAX_SOURCES, CAL_E_INVALID, "cal_fuse_combine: n_src %d", a->n_src);
+  CAL_REQUIRE(a->C_pad % 8 == 0 && a->B >= 1 && a->H >= 1 && a->W >= 1, CAL_E_INVALID, "cal_fuse_combine: bad shape");
+  CombineParams p{};
+  p.y = reinterpret_cast<__half*>(a->y);
+  p.B = a->B; p.H = a->H; p.W = a->W; p.C8 = a->C_pad / 8;
+  p.n_src = a->n_src;
+  for (int i = 0; i < a->n_src; ++i) {
+    CAL_REQUIRE(a->src[i] && a->src_h[i] >= 1 && a->src_w[i] >= 1, CAL_E_INVALID, "cal_fuse_combine: bad source %d", i);
+    p.src[i] = reinterpret_cast<const __half*>(a->src[i]);
+    p.sh[i] = a->src_h[i];
+    p.sw[i] = a->src_w[i];
+    // fp32 scale exactly as ATen's area_pixel_compute_scale<float>(in, out, align_corners=true)
+    p.scale_y[i] = a->H > 1 ? static_cast<float>(a->src_h[i] - 1) / static_cast<float>(a->H - 1) : 0.0f;
+    p.scale_x[i] = a->W > 1 ? static_cast<float>(a->src_w[i] - 1) / static_cast<float>(a->W - 1) : 0.0f;
+  }
+  p.bias = a->bias;
+  p.relu = a->relu;
+  const long long total = static_cast<long long>(a->B) * a->H * a->W * p.C8;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 148ll * 16;
+  if (blocks > cap) blocks = cap;
+  fuse_combine_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}

@@ -1,0 +1,136 @@
+"""Thin torch-tensor wrappers over the C-ABI ops.  PyTorch is only the container for
+device memory and the source of the CUDA stream; all arithmetic runs in the
+hand-written kernels of csrc/."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor, dtype, what: str) -> int:
+    if not t.is_cuda:
+        raise _lib.CalError(f"{what}: tensor must live on a CUDA device (no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.CalError(f"{what}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.CalError(f"{what}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def kp_decode(logp: torch.Tensor, size) -> torch.Tensor:
+    """(B,C,h,w) fp32 log-probs -> (B,C-1,3) [x,y,conf] (transforms.py:228-239)."""
+    B, Cc, h, w = logp.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((B, max(Cc - 1, 0), 3), dtype=torch.float32, device=logp.device)
+    if B == 0 or Cc <= 1:
+        return out
+    with torch.cuda.device(logp.device):
+        st = _lib.lib().cal_kp_decode(_dev(logp, torch.float32, "kp_decode"), B, Cc, h, w, H, W,
+                                      out.data_ptr(), _stream())
+    _lib.check(st, "cal_kp_decode")
+    return out
+
+
+def line_decode(heat: torch.Tensor, sigma: float, scale: float = 1.0) -> torch.Tensor:
+    """(B,C,h,w) fp32 probabilities -> (B,C,2,3) two peaks per channel
+    (line/transforms.py:224-280)."""
+    B, Cc, h, w = heat.shape
+    out = torch.empty((B, Cc, 2, 3), dtype=torch.float32, device=heat.device)
+    if B == 0 or Cc == 0:
+        return out
+    with torch.cuda.device(heat.device):
+        st = _lib.lib().cal_line_decode(_dev(heat, torch.float32, "line_decode"), B, Cc, h, w,
+                                        float(sigma), float(scale), out.data_ptr(), _stream())
+    _lib.check(st, "cal_line_decode")
+    return out
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *,
+           ksize: int, stride: int, cout_rows: int, relu: bool, res: Optional[torch.Tensor] = None,
+           mode: int = 0, n_classes: int = 0) -> torch.Tensor:
+    """x: fp16 NHWC (B,Hin,Win,Cin_pad); w: fp16 (Cout_rows, taps*Cin_pad);
+    y: fp16 NHWC (B,Hout,Wout,Cout_pad) or fp32 NCHW (B,n_classes,Hout,Wout) for mode 1/2."""
+    B, Hin, Win, Cin = x.shape
+    a = _lib.ConvArgs()
+    a.x = _dev(x, torch.float16, "conv2d x")
+    a.w = _dev(w, torch.float16, "conv2d w")
+    a.bias = _dev(bias, torch.float32, "conv2d bias") if bias is not None else None
+    a.res = _dev(res, torch.float16, "conv2d res") if res is not None else None
+    if mode == 0:
+        a.y = _dev(y, torch.float16, "conv2d y")
+        _, Hout, Wout, Cout_pad = y.shape
+        if res is not None and tuple(res.shape) != tuple(y.shape):
+            raise _lib.CalError("conv2d: residual shape mismatch")
+    else:
+        a.y = _dev(y, torch.float32, "conv2d y")
+        _, ncls, Hout, Wout = y.shape
+        if ncls != n_classes:
+            raise _lib.CalError("conv2d: n_classes mismatch")
+        Cout_pad = 64
+    if w.shape[0] != cout_rows or w.shape[1] != ksize * ksize * Cin:
+        raise _lib.CalError(f"conv2d: weight shape {tuple(w.shape)} vs rows {cout_rows}, K {ksize * ksize * Cin}")
+    if bias is not None and bias.numel() != Cout_pad:
+        raise _lib.CalError("conv2d: bias length must equal Cout_pad")
+    a.B, a.Hin, a.Win, a.Cin_pad = B, Hin, Win, Cin
+    a.Hout, a.Wout, a.Cout_pad, a.Cout_rows = Hout, Wout, Cout_pad, cout_rows
+    a.ksize, a.stride, a.relu, a.mode, a.n_classes = ksize, stride, int(relu), mode, n_classes
+    with torch.cuda.device(x.device):
+        st = _lib.lib().cal_conv2d(C.byref(a), _stream())
+    _lib.check(st, "cal_conv2d")
+    return y
+
+
+def stem_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """x fp32 NCHW (B,3,H,W); w fp32 (64,27); y fp16 NHWC (B,Ho,Wo,64)."""
+    B, _, H, W = x.shape
+    _, Ho, Wo, _ = y.shape
+    with torch.cuda.device(x.device):
+        st = _lib.lib().cal_stem_conv(_dev(x, torch.float32, "stem x"), _dev(w, torch.float32, "stem w"),
+                                      _dev(bias, torch.float32, "stem bias"), _dev(y, torch.float16, "stem y"),
+                                      B, H, W, Ho, Wo, _stream())
+    _lib.check(st, "cal_stem_conv")
+    return y
+
+
+def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[torch.Tensor] = None,
+                 relu: bool = False) -> torch.Tensor:
+    """y = [relu](bias + sum_i up_i(src_i)); all fp16 NHWC with the same C_pad; sources of a
+    different spatial size are bilinearly resampled (align_corners=True)."""
+    B, H, W, Cp = y.shape
+    a = _lib.CombineArgs()
+    a.y = _dev(y, torch.float16, "combine y")
+    a.B, a.H, a.W, a.C_pad = B, H, W, Cp
+    a.n_src = len(srcs)
+    if not 1 <= len(srcs) <= _lib.CAL_MAX_SOURCES:
+        raise _lib.CalError("fuse_combine: 1..6 sources")
+    for i, s in enumerate(srcs):
+        if s.shape[0] != B or s.shape[3] != Cp:
+            raise _lib.CalError("fuse_combine: source batch/channel mismatch")
+        a.src[i] = _dev(s, torch.float16, "combine src")
+        a.src_h[i], a.src_w[i] = s.shape[1], s.shape[2]
+    a.bias = _dev(bias, torch.float32, "combine bias") if bias is not None else None
+    a.relu = int(relu)
+    with torch.cuda.device(y.device):
+        st = _lib.lib().cal_fuse_combine(C.byref(a), _stream())
+    _lib.check(st, "cal_fuse_combine")
+    return y
+
+
+def tma_probe(x: torch.Tensor, box_w: int, box_h: int, estride: int, c0: int, x0: int, y0: int,
+              n0: int) -> torch.Tensor:
+    """Raw 16 KiB shared-memory image of one activation TMA box (tests only)."""
+    B, H, W, Cc = x.shape
+    out = torch.empty(16384, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.lib().cal_debug_tma_probe(_dev(x, torch.float16, "probe x"), B, H, W, Cc, box_w, box_h,
+                                            estride, c0, x0, y0, n0, out.data_ptr(), _stream())
+    _lib.check(st, "cal_debug_tma_probe")
+    return out

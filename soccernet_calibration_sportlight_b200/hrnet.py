@@ -1,0 +1,433 @@
+"""HRNetV2 heat-map networks on the B200 kernels, behind the reference's module API.
+
+Mirrors (names, constructor arguments, call signature, state_dict keys):
+  * ``HRNetHeatmap``  - src/models/hrnet/model.py:130-150 (keypoints, 58 log-prob maps at
+    H/2 x W/2) and src/models/line/model.py:127-147 (lines, 23 prob maps at H/4 x W/4);
+  * the layer schedule of ``HighResolutionNet.forward`` - src/models/hrnet/hrnet.py:437-511,
+    src/models/line/hrnet.py:185-249, with ``HighResolutionModule.forward`` hrnet.py:222-246.
+
+What runs where: this file only walks the architecture and launches kernels through the
+C ABI (ops.py); every conv/BN/ReLU/add is one ``cal_conv2d`` launch (tcgen05 implicit GEMM,
+BN folded, residual and ReLU in the epilogue), every multi-resolution sum one
+``cal_fuse_combine`` launch.  Activations are fp16 NHWC, channels padded to 64.
+
+Head restructuring (exact in real arithmetic): the 1x1 conv of the head
+commutes with the bilinear upsampling, so it is applied per branch at the branch's own
+resolution and only the stem part runs at full resolution; the concatenated 784-channel
+tensor (hrnet.py:509) is never materialised.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops, packing
+
+EXPANSION = {"BASIC": 1, "BOTTLENECK": 4}
+
+
+class Config(dict):
+    """dict with attribute access; supports ``'upscale' in config`` and ``config.upscale``
+    like the objects the reference builds from its YAML files (hrnet.py:306-315)."""
+
+    def __getattr__(self, k):
+        try:
+            v = self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+        return Config(v) if isinstance(v, dict) and not isinstance(v, Config) else v
+
+
+def _stage(nm, nb, bt, blocks, ch):
+    return dict(num_modules=nm, num_branches=nb, block_type=bt, num_blocks=blocks, num_channels=ch)
+
+
+def w48_config(kind: str = "keypoints") -> Config:
+    """model_config/hrnet_w48.yaml of the keypoint (hrnet/) or line (line/) model."""
+    cfg = dict(stem_width=64, final_conv_kernel=1, pretrain="",
+               stage1=_stage(1, 1, "BOTTLENECK", [4], [64]),
+               stage2=_stage(1, 2, "BASIC", [4, 4], [48, 96]),
+               stage3=_stage(4, 3, "BASIC", [4, 4, 4], [48, 96, 192]),
+               stage4=_stage(3, 4, "BASIC", [4, 4, 4, 4], [48, 96, 192, 384]))
+    if kind == "keypoints":
+        cfg.update(num_classes=58, upscale=2, internal_final_conv=0)
+    elif kind == "lines":
+        cfg.update(num_classes=23)
+    else:
+        raise ValueError(kind)
+    return Config(cfg)
+
+
+# ------------------------------------------------------------------------- architecture walk
+class _Conv:
+    """One conv(+BN) of the reference, identified by its state_dict prefixes."""
+    __slots__ = ("conv", "bn", "cin", "cout", "k", "s", "has_bias")
+
+    def __init__(self, conv, bn, cin, cout, k, s, has_bias=False):
+        self.conv, self.bn, self.cin, self.cout, self.k, self.s, self.has_bias = conv, bn, cin, cout, k, s, has_bias
+
+
+def _walk(cfg: Config, kind: str):
+    """Enumerates the network as nested python structures of _Conv, in state_dict order."""
+    net: Dict[str, object] = {}
+    sw = cfg.stem_width
+    net["conv1"] = _Conv("conv1", "bn1", 3, sw, 3, 2)
+    net["conv2"] = _Conv("conv2", "bn2", sw, sw, 3, 2)
+
+    def block_list(prefix, block_type, cin, planes, n):
+        blocks = []
+        exp = EXPANSION[block_type]
+        for i in range(n):
+            p = f"{prefix}.{i}"
+            ci = cin if i == 0 else planes * exp
+            if block_type == "BOTTLENECK":
+                convs = [_Conv(f"{p}.conv1", f"{p}.bn1", ci, planes, 1, 1),
+                         _Conv(f"{p}.conv2", f"{p}.bn2", planes, planes, 3, 1),
+                         _Conv(f"{p}.conv3", f"{p}.bn3", planes, planes * 4, 1, 1)]
+            else:
+                convs = [_Conv(f"{p}.conv1", f"{p}.bn1", ci, planes, 3, 1),
+                         _Conv(f"{p}.conv2", f"{p}.bn2", planes, planes, 3, 1)]
+            ds = None
+            if i == 0 and ci != planes * exp:
+                ds = _Conv(f"{p}.downsample.0", f"{p}.downsample.1", ci, planes * exp, 1, 1)
+            blocks.append((convs, ds))
+        return blocks
+
+    s1 = cfg.stage1
+    net["layer1"] = block_list("layer1", s1.block_type, 64, s1.num_channels[0], s1.num_blocks[0])
+    pre = [EXPANSION[s1.block_type] * s1.num_channels[0]]
+    for idx in (2, 3, 4):
+        sc = cfg[f"stage{idx}"]
+        exp = EXPANSION[sc["block_type"]]
+        ch = [c * exp for c in sc["num_channels"]]
+        # transition (hrnet.py:357-391)
+        trans = []
+        for i, c in enumerate(ch):
+            tp = f"transition{idx - 1}.{i}"
+            if i < len(pre):
+                trans.append(None if c == pre[i] else [_Conv(f"{tp}.0", f"{tp}.1", pre[i], c, 3, 1)])
+            else:
+                chain = []
+                for j in range(i + 1 - len(pre)):
+                    co = c if j == i - len(pre) else pre[-1]
+                    chain.append(_Conv(f"{tp}.{j}.0", f"{tp}.{j}.1", pre[-1], co, 3, 2))
+                trans.append(chain)
+        net[f"transition{idx - 1}"] = trans
+        modules = []
+        for m in range(sc["num_modules"]):
+            mp = f"stage{idx}.{m}"
+            branches = [block_list(f"{mp}.branches.{b}", sc["block_type"], ch[b], ch[b] // exp, sc["num_blocks"][b])
+                        for b in range(len(ch))]
+            fuse = []
+            for i in range(len(ch)):
+                row = []
+                for j in range(len(ch)):
+                    fp = f"{mp}.fuse_layers.{i}.{j}"
+                    if j == i:
+                        row.append(None)
+                    elif j > i:
+                        row.append([_Conv(f"{fp}.0", f"{fp}.1", ch[j], ch[i], 1, 1)])
+                    else:
+                        chain = []
+                        for k in range(i - j):
+                            co = ch[i] if k == i - j - 1 else ch[j]
+                            chain.append(_Conv(f"{fp}.{k}.0", f"{fp}.{k}.1", ch[j], co, 3, 2))
+                        row.append(chain)
+                fuse.append(row)
+            modules.append((branches, fuse))
+        net[f"stage{idx}"] = modules
+        pre = ch
+    upscale = cfg["upscale"] if ("upscale" in cfg and cfg["upscale"] > 1) else 1
+    if kind == "lines":
+        upscale = 1
+    last_in = sum(pre) + (sw if upscale > 1 else 0)
+    net["last_in"] = last_in
+    net["upscale"] = upscale
+    net["branch_channels"] = pre
+    net["head1"] = _Conv("last_layer.0", "last_layer.1", last_in, last_in, 1, 1, has_bias=True)
+    net["head2"] = _Conv("last_layer.3", None, last_in, cfg.num_classes, cfg.final_conv_kernel, 1, has_bias=True)
+    return net
+
+
+def _all_convs(net) -> List[_Conv]:
+    out: List[_Conv] = [net["conv1"], net["conv2"]]
+
+    def blocks(bl):
+        for convs, ds in bl:
+            out.extend(convs)
+            if ds is not None:
+                out.append(ds)
+
+    blocks(net["layer1"])
+    for idx in (2, 3, 4):
+        for t in net[f"transition{idx - 1}"]:
+            if t:
+                out.extend(t)
+        for branches, fuse in net[f"stage{idx}"]:
+            for b in branches:
+                blocks(b)
+            for row in fuse:
+                for cell in row:
+                    if cell:
+                        out.extend(cell)
+    out.extend([net["head1"], net["head2"]])
+    return out
+
+
+def state_dict_schema(cfg: Config, kind: str, prefix: str = "model.") -> "OrderedDict[str, Tuple[int, ...]]":
+    """Keys and shapes of the reference's ``nn_state_dict`` for this architecture
+    (pinned by tests/golden/hrnet_state_keys.json)."""
+    net = _walk(cfg, kind)
+    sd: "OrderedDict[str, Tuple[int, ...]]" = OrderedDict()
+
+    def add(c: _Conv):
+        sd[f"{prefix}{c.conv}.weight"] = (c.cout, c.cin, c.k, c.k)
+        if c.has_bias:
+            sd[f"{prefix}{c.conv}.bias"] = (c.cout,)
+        if c.bn:
+            for n in ("weight", "bias", "running_mean", "running_var"):
+                sd[f"{prefix}{c.bn}.{n}"] = (c.cout,)
+            sd[f"{prefix}{c.bn}.num_batches_tracked"] = ()
+    # state_dict order: convN before bnN for blocks (conv1,bn1,conv2,bn2,...), which the
+    # generic add() reproduces; the stem is conv1,bn1,conv2,bn2 as well.
+    for c in _all_convs(net):
+        add(c)
+    return sd
+
+
+def init_state_dict(cfg: Config, kind: str, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded random weights of the right shapes (no trained weights ship with the
+    reference): He-style conv weights, non-trivial BN statistics."""
+    g = torch.Generator().manual_seed(seed)
+    sd: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+    for k, shape in state_dict_schema(cfg, kind).items():
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif len(shape) == 4:
+            fan = shape[1] * shape[2] * shape[3]
+            sd[k] = torch.randn(shape, generator=g) * math.sqrt(1.0 / fan)
+        elif k.endswith("running_var"):
+            sd[k] = 0.5 + torch.rand(shape, generator=g)
+        elif k.endswith("running_mean") or ".bias" in k:
+            sd[k] = 0.1 * torch.randn(shape, generator=g)
+        else:  # BN weight
+            sd[k] = 0.8 + 0.4 * torch.rand(shape, generator=g)
+    return sd
+
+
+# ------------------------------------------------------------------------------- the engine
+class _Packed:
+    __slots__ = ("w", "b", "rows", "cin_pad", "cout_pad", "k", "s")
+
+
+class HRNetHeatmap:
+    """Drop-in for ``HRNetHeatmap`` (model.py:130-150 / line/model.py:127-147).
+
+    ``hrnet_config`` is the reference's model config (mapping or attribute object);
+    ``num_refinement_stages`` must be 0 (every shipped config, train_config.yaml:34).
+    ``forward(x)`` takes (B,3,H,W) fp32 in [0,1] and returns a list with one fp32 tensor
+    (B,num_classes,H/2,W/2) log-probs (keypoints) or (B,num_classes,H/4,W/4) probs (lines).
+    """
+
+    def __init__(self, hrnet_config, num_refinement_stages: int = 0, num_heatmaps: int = 38,
+                 kind: Optional[str] = None):
+        if num_refinement_stages != 0:
+            raise NotImplementedError("refinement stages are disabled in every shipped config")
+        cfg = hrnet_config if isinstance(hrnet_config, Config) else Config(
+            {k: hrnet_config[k] for k in hrnet_config} if hasattr(hrnet_config, "keys") else vars(hrnet_config))
+        if kind is None:
+            kind = "keypoints" if ("upscale" in cfg and cfg["upscale"] > 1) else "lines"
+        self.kind = kind
+        self.cfg = cfg
+        self.net = _walk(cfg, kind)
+        self.num_classes = int(cfg["num_classes"])
+        self._sd: Optional[Dict[str, torch.Tensor]] = None
+        self._packed: Dict[str, _Packed] = {}
+        self.device: Optional[torch.device] = None
+        self.training = False
+
+    # -- nn.Module-like surface used by the reference's callers
+    def eval(self):
+        self.training = False
+        return self
+
+    def state_dict(self):
+        if self._sd is None:
+            self.load_state_dict(init_state_dict(self.cfg, self.kind))
+        return self._sd
+
+    def load_state_dict(self, sd, strict: bool = True):
+        schema = state_dict_schema(self.cfg, self.kind)
+        sd = {k.replace("_orig_mod.", ""): v for k, v in sd.items()}  # metamodel.py:113-117
+        missing = [k for k in schema if k not in sd]
+        if missing and strict:
+            raise KeyError(f"missing {len(missing)} keys, e.g. {missing[:3]}")
+        for k, shape in schema.items():
+            if k in sd and tuple(sd[k].shape) != tuple(shape):
+                raise ValueError(f"{k}: shape {tuple(sd[k].shape)} != {shape}")
+        self._sd = OrderedDict((k, sd[k].detach().clone().cpu()) for k in schema if k in sd)
+        self._packed = {}
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("HRNetHeatmap runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.device = device
+        self._pack()
+        return self
+
+    def cuda(self, idx: int = 0):
+        return self.to(f"cuda:{idx}")
+
+    # -- weight preparation
+    def _bn(self, name):
+        sd = self._sd
+        return {k: sd[f"model.{name}.{k}"] for k in ("weight", "bias", "running_mean", "running_var")}
+
+    def _fold(self, c: _Conv):
+        sd = self._sd
+        w = sd[f"model.{c.conv}.weight"]
+        b = sd.get(f"model.{c.conv}.bias") if c.has_bias else None
+        return packing.fold_bn(w, b, self._bn(c.bn) if c.bn else None)
+
+    def _put(self, key, w, b, k, s, cout_pad=None):
+        wp, bp, rows = packing.pack_conv(w, b, cout_pad=cout_pad)
+        p = _Packed()
+        p.w, p.b, p.rows = wp.to(self.device), bp.to(self.device), rows
+        p.cin_pad, p.cout_pad, p.k, p.s = packing.pad_to(w.shape[1]), bp.numel(), k, s
+        self._packed[key] = p
+
+    def _pack(self):
+        if self._sd is None:
+            self.load_state_dict(init_state_dict(self.cfg, self.kind))
+        net = self.net
+        for c in _all_convs(net):
+            if c is net["conv1"] or c is net["head1"] or c is net["head2"]:
+                continue
+            w, b = self._fold(c)
+            self._put(c.conv, w, b, c.k, c.s)
+        # stem conv1: fp32 CUDA-core kernel, (64, 27) [co][ci*9+ky*3+kx]
+        w, b = self._fold(net["conv1"])
+        self.stem_w = w.reshape(w.shape[0], 27).float().contiguous().to(self.device)
+        self.stem_b = b.float().contiguous().to(self.device)
+        # head: split the first 1x1 conv by source (hrnet.py:509 concat order)
+        w1, b1 = self._fold(net["head1"])
+        cpad = packing.pad_to(net["last_in"])
+        srcs = ([("stem", self.cfg.stem_width)] if net["upscale"] > 1 else []) + \
+               [(f"b{i}", c) for i, c in enumerate(net["branch_channels"])]
+        off = 0
+        zero = torch.zeros(w1.shape[0], dtype=torch.float64)
+        for name, c in srcs:
+            self._put(f"head1.{name}", w1[:, off:off + c], zero, 1, 1, cout_pad=cpad)
+            off += c
+        b1p = torch.zeros(cpad, dtype=torch.float32)
+        b1p[:w1.shape[0]] = b1.float()
+        self.head_b1 = b1p.to(self.device)
+        w2, b2 = self._fold(net["head2"])
+        if w2.shape[-1] != 1:
+            raise NotImplementedError("final_conv_kernel must be 1 (every shipped config)")
+        self._put("head2", w2, b2, 1, 1, cout_pad=64)
+
+    # -- launch helpers
+    def _conv(self, x, key, relu, res=None):
+        p = self._packed[key]
+        B, H, W, _ = x.shape
+        pad = p.k // 2
+        Ho, Wo = (H + 2 * pad - p.k) // p.s + 1, (W + 2 * pad - p.k) // p.s + 1
+        y = torch.empty((B, Ho, Wo, p.cout_pad), dtype=torch.float16, device=x.device)
+        return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res)
+
+    def _blocks(self, x, blocks):
+        for convs, ds in blocks:
+            r = x if ds is None else self._conv(x, ds.conv, relu=False)
+            t = x
+            for c in convs[:-1]:
+                t = self._conv(t, c.conv, relu=True)
+            x = self._conv(t, convs[-1].conv, relu=True, res=r)
+        return x
+
+    def _module(self, xs, module):
+        branches, fuse = module
+        xs = [self._blocks(x, b) for x, b in zip(xs, branches)]
+        nb = len(xs)
+        outs = []
+        for i in range(nb):
+            # same-resolution terms chained through conv epilogues: x_i + sum_{j<i} down_ij(x_j)
+            has_up = i < nb - 1
+            r = xs[i]
+            for j in range(i):
+                t = xs[j]
+                chain = fuse[i][j]
+                for c in chain[:-1]:
+                    t = self._conv(t, c.conv, relu=True)
+                last_term = (j == i - 1)
+                r = self._conv(t, chain[-1].conv, relu=(last_term and not has_up), res=r)
+            if has_up:
+                ups = [self._conv(xs[j], fuse[i][j][0].conv, relu=False) for j in range(i + 1, nb)]
+                y = torch.empty_like(xs[i])
+                r = ops.fuse_combine(y, [r] + ups, None, relu=True)
+            outs.append(r)
+        return outs
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        if self.device is None:
+            raise RuntimeError("call .to('cuda:N') first")
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        x = x.contiguous().float()
+        net = self.net
+        B, _, H, W = x.shape
+        with torch.cuda.device(self.device):
+            Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            stem = torch.empty((B, Ho, Wo, 64), dtype=torch.float16, device=self.device)
+            ops.stem_conv(x, self.stem_w, self.stem_b, stem)
+            t = self._conv(stem, "conv2", relu=True)
+            t = self._blocks(t, net["layer1"])
+            ys = [t]
+            for idx in (2, 3, 4):
+                trans = net[f"transition{idx - 1}"]
+                nprev = len(ys)
+                xs = []
+                for i, tr in enumerate(trans):
+                    if tr is None:
+                        xs.append(ys[i])
+                    else:
+                        v = ys[i] if i < nprev else ys[-1]
+                        for c in tr:
+                            v = self._conv(v, c.conv, relu=True)
+                        xs.append(v)
+                for module in net[f"stage{idx}"]:
+                    xs = self._module(xs, module)
+                ys = xs
+            return [self._head(stem, ys)]
+
+    __call__ = forward
+
+    def _head(self, stem, ys):
+        net = self.net
+        up = net["upscale"]
+        h, w = ys[0].shape[1] * up, ys[0].shape[2] * up
+        B = ys[0].shape[0]
+        cpad = self.head_b1.numel()
+        if up > 1:
+            full, full_key, low = stem, "head1.stem", list(enumerate(ys))
+            if stem.shape[1] != h or stem.shape[2] != w:
+                raise NotImplementedError("stem feature must already be at head resolution (hrnet.py:495-500)")
+        else:
+            full, full_key, low = ys[0], "head1.b0", list(enumerate(ys))[1:]
+        proj = [self._conv(y, f"head1.b{i}", relu=False) for i, y in low]
+        u = torch.empty((B, h, w, cpad), dtype=torch.float16, device=self.device)
+        ops.fuse_combine(u, proj, self.head_b1, relu=False)
+        del proj
+        z = self._conv(full, full_key, relu=True, res=u)
+        del u
+        p2 = self._packed["head2"]
+        heat = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=self.device)
+        ops.conv2d(z, p2.w, p2.b, heat, ksize=1, stride=1, cout_rows=p2.rows, relu=False,
+                   mode=1 if self.kind == "keypoints" else 2, n_classes=self.num_classes)
+        return heat

@@ -164,6 +164,12 @@ int cal_debug_tma_probe(const void* x, int B, int H, int W, int C, int box_w, in
                         int estride, int c0, int x0, int y0, int n0, void* out_smem_16k,
                         void* stream);
 
+/* Experiment pinning a hardware convention the 3x3 kernel relies on: a SWIZZLE_128B K-major
+ * operand descriptor whose start address is shifted by whole 128-byte rows.
+ * D(128x64 fp32) = X[shift : shift+128, :] * W^T with X (256,64), W (64,64) fp16. */
+int cal_debug_shift_mma(const void* x_256x64, const void* w_64x64, int shift,
+                        int base_offset_mode, float* out_128x64, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ CAL_MAX_SOURCES = 6
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_fuse_combine", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
-    "cal_debug_tma_probe",
+    "cal_debug_tma_probe", "cal_debug_shift_mma",
 ]
 
 
@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.cal_stem_conv.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]
     L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    L.cal_debug_shift_mma.argtypes = [vp, vp, i32, i32, vp, vp]
     if hasattr(L, "cal_camera_solve"):
         L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
         L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]

@@ -274,6 +274,55 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0,
   for (int i = threadIdx.x; i < A_STAGE_BYTES / 16; i += blockDim.x) out[i] = reinterpret_cast<uint4*>(smem)[i];
 }
 
+
+// Experiment: is an M-row-shifted start address legal for a SWIZZLE_128B K-major operand?
+// A_full = 256 rows x 64 fp16 loaded by one TMA box; D = A_full[shift : shift+128] * W^T.
+__global__ void shift_mma_probe_kernel(const __grid_constant__ CUtensorMap tmX,
+                                       const __grid_constant__ CUtensorMap tmW, int shift,
+                                       int base_offset_mode, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 256 x 128 B
+  uint8_t* sB = smem + 256 * 128;     // 64 x 128 B
+  __shared__ uint64_t bar, mbar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&mbar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tslot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tslot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 256 * 128 + 64 * 128);
+    tma_load_2d(sA, &tmX, &bar, 0, 0);
+    tma_load_2d(sB, &tmW, &bar, 0, 0);
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sA) + shift * 128;
+    uint64_t a_desc = make_smem_desc(a_addr, 128, 2);
+    if (base_offset_mode == 1) a_desc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+    const uint64_t b_desc = make_smem_desc(smem_u32(sB), 128, 2);
+    const uint32_t idesc = make_idesc_f16(128, 64);
+    for (int kk = 0; kk < 4; ++kk) umma_f16(tmem_base, a_desc + 2 * kk, b_desc + 2 * kk, idesc, kk != 0);
+    umma_commit(&mbar);
+  }
+  mbar_wait(&mbar, 0);
+  tc_fence_after();
+  if (warp < 4) {
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int g = 0; g < 4; ++g) {
+      uint32_t r[16];
+      tmem_ld16(taddr + g * 16, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 64 + g * 16 + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
 int make_act_tmap(CUtensorMap* tm, const void* x, int B, int H, int W, int C, int box_w, int box_h,
                   int estride) {
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -385,6 +434,25 @@ extern "C" int cal_debug_tma_probe(const void* x, int B, int H, int W, int C, in
   CAL_CHECK_CUDA(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024));
   tma_probe_kernel<<<1, 128, A_STAGE_BYTES + 1024, static_cast<cudaStream_t>(stream)>>>(
       tm, c0, x0, y0, n0, (uint32_t)(nx * ny * 128), reinterpret_cast<uint4*>(out_smem_16k));
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_debug_shift_mma(const void* x_256x64, const void* w_64x64, int shift,
+                                   int base_offset_mode, float* out_128x64, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(x_256x64 && w_64x64 && out_128x64 && shift >= 0 && shift <= 128, CAL_E_INVALID,
+              "cal_debug_shift_mma: bad args");
+  CUtensorMap tmX, tmW;
+  const uint64_t dx[2] = {64, 256}, dw[2] = {64, 64}, st[1] = {128};
+  const uint32_t bx[2] = {64, 256}, bw[2] = {64, 64};
+  int rc = encode_tmap_f16(&tmX, x_256x64, 2, dx, st, bx, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != CAL_OK) return rc;
+  rc = encode_tmap_f16(&tmW, w_64x64, 2, dw, st, bw, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != CAL_OK) return rc;
+  CAL_CHECK_CUDA(cudaFuncSetAttribute(shift_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  shift_mma_probe_kernel<<<1, 128, 256 * 128 + 64 * 128 + 1024, static_cast<cudaStream_t>(stream)>>>(
+      tmX, tmW, shift, base_offset_mode, out_128x64);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
 }

@@ -177,6 +177,50 @@ def _all_convs(net) -> List[_Conv]:
     return out
 
 
+def conv_shapes(kind: str, H: int, W: int, cfg: Optional[Config] = None):
+    """[(conv, Hout, Wout)] of every convolution of the reference's forward at an H x W input
+    (hrnet.py:437-511 / line/hrnet.py:185-249), AS WRITTEN there (head 1x1 at full head
+    resolution over the concatenated channels) - the algorithmic work list."""
+    cfg = w48_config(kind) if cfg is None else cfg
+    net = _walk(cfg, kind)
+    dn = lambda v: (v - 1) // 2 + 1
+    h1, w1 = dn(H), dn(W)
+    h2, w2 = dn(h1), dn(w1)
+    out = [(net["conv1"], h1, w1), (net["conv2"], h2, w2)]
+    for convs, ds in net["layer1"]:
+        out += [(c, h2, w2) for c in convs] + ([(ds, h2, w2)] if ds is not None else [])
+    sizes = [(h2, w2)]
+    for idx in (2, 3, 4):
+        trans = net[f"transition{idx - 1}"]
+        while len(sizes) < len(trans):
+            sizes.append((dn(sizes[-1][0]), dn(sizes[-1][1])))
+        for i, tr in enumerate(trans):
+            if tr:
+                out += [(c, *sizes[i]) for c in tr]
+        for branches, fuse in net[f"stage{idx}"]:
+            for b, bl in enumerate(branches):
+                for convs, ds in bl:
+                    out += [(c, *sizes[b]) for c in convs]
+            for i, row in enumerate(fuse):
+                for j, cell in enumerate(row):
+                    if not cell:
+                        continue
+                    if j > i:
+                        out.append((cell[0], *sizes[j]))
+                    else:
+                        for k, c in enumerate(cell):
+                            out.append((c, *sizes[j + k + 1]))
+    hh, wh = sizes[0][0] * net["upscale"], sizes[0][1] * net["upscale"]
+    out += [(net["head1"], hh, wh), (net["head2"], hh, wh)]
+    return out
+
+
+def conv_gflop_per_frame(kind: str, H: int = 540, W: int = 960) -> float:
+    """2*MAC of the reference's convolutions per frame, in GFLOP (507.82 for the
+    keypoint net, 371.4 for the line net at 960x540).  roofline.achieved is computed from this."""
+    return sum(2.0 * c.cin * c.cout * c.k * c.k * h * w for c, h, w in conv_shapes(kind, H, W)) / 1e9
+
+
 def state_dict_schema(cfg: Config, kind: str, prefix: str = "model.") -> "OrderedDict[str, Tuple[int, ...]]":
     """Keys and shapes of the reference's ``nn_state_dict`` for this architecture
     (pinned by tests/golden/hrnet_state_keys.json)."""
@@ -417,7 +461,9 @@ class HRNetHeatmap:
         if up > 1:
             full, full_key, low = stem, "head1.stem", list(enumerate(ys))
             if stem.shape[1] != h or stem.shape[2] != w:
-                raise NotImplementedError("stem feature must already be at head resolution (hrnet.py:495-500)")
+                # odd input sizes: the reference resamples x_stem to the head size (hrnet.py:495-498)
+                rs = torch.empty((B, h, w, stem.shape[3]), dtype=torch.float16, device=self.device)
+                full = ops.fuse_combine(rs, [stem], None, relu=False)
         else:
             full, full_key, low = ys[0], "head1.b0", list(enumerate(ys))[1:]
         proj = [self._conv(y, f"head1.b{i}", relu=False) for i, y in low]

@@ -11,8 +11,38 @@ import torch
 from . import _lib
 
 
+LAUNCHES = 0          # kernels launched through this module (bench.py reports it)
+PROFILE = None        # when a list: (kernel name, start event, end event) per launch
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+class _Launch:
+    """Counts one kernel launch and, in profiling mode, brackets it with CUDA events on the
+    launching stream."""
+
+    def __init__(self, name: str, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += 1
+        self.ctx = torch.cuda.device(self.device)
+        self.ctx.__enter__()
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e1.record()
+            PROFILE.append((self.name, self.e0, self.e1))
+        self.ctx.__exit__(*exc)
+        return False
 
 
 def _dev(t: torch.Tensor, dtype, what: str) -> int:
@@ -29,11 +59,14 @@ def kp_decode(logp: torch.Tensor, size) -> torch.Tensor:
     """(B,C,h,w) fp32 log-probs -> (B,C-1,3) [x,y,conf] (transforms.py:228-239)."""
     B, Cc, h, w = logp.shape
     H, W = int(size[0]), int(size[1])
+    if not logp.is_cuda:
+        raise _lib.CalError("kp_decode: tensor must live on a CUDA device (no CPU fallback)")
     out = torch.empty((B, max(Cc - 1, 0), 3), dtype=torch.float32, device=logp.device)
     if B == 0 or Cc <= 1:
         return out
-    with torch.cuda.device(logp.device):
-        st = _lib.lib().cal_kp_decode(_dev(logp, torch.float32, "kp_decode"), B, Cc, h, w, H, W,
+    ptr = _dev(logp, torch.float32, "kp_decode")
+    with _Launch("kp_decode", logp.device):
+        st = _lib.lib().cal_kp_decode(ptr, B, Cc, h, w, H, W,
                                       out.data_ptr(), _stream())
     _lib.check(st, "cal_kp_decode")
     return out
@@ -43,11 +76,14 @@ def line_decode(heat: torch.Tensor, sigma: float, scale: float = 1.0) -> torch.T
     """(B,C,h,w) fp32 probabilities -> (B,C,2,3) two peaks per channel
     (line/transforms.py:224-280)."""
     B, Cc, h, w = heat.shape
+    if not heat.is_cuda:
+        raise _lib.CalError("line_decode: tensor must live on a CUDA device (no CPU fallback)")
     out = torch.empty((B, Cc, 2, 3), dtype=torch.float32, device=heat.device)
     if B == 0 or Cc == 0:
         return out
-    with torch.cuda.device(heat.device):
-        st = _lib.lib().cal_line_decode(_dev(heat, torch.float32, "line_decode"), B, Cc, h, w,
+    ptr = _dev(heat, torch.float32, "line_decode")
+    with _Launch("line_decode", heat.device):
+        st = _lib.lib().cal_line_decode(ptr, B, Cc, h, w,
                                         float(sigma), float(scale), out.data_ptr(), _stream())
     _lib.check(st, "cal_line_decode")
     return out
@@ -82,7 +118,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
     a.B, a.Hin, a.Win, a.Cin_pad = B, Hin, Win, Cin
     a.Hout, a.Wout, a.Cout_pad, a.Cout_rows = Hout, Wout, Cout_pad, cout_rows
     a.ksize, a.stride, a.relu, a.mode, a.n_classes = ksize, stride, int(relu), mode, n_classes
-    with torch.cuda.device(x.device):
+    with _Launch("conv_tc", x.device):
         st = _lib.lib().cal_conv2d(C.byref(a), _stream())
     _lib.check(st, "cal_conv2d")
     return y
@@ -92,7 +128,7 @@ def stem_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Ten
     """x fp32 NCHW (B,3,H,W); w fp32 (64,27); y fp16 NHWC (B,Ho,Wo,64)."""
     B, _, H, W = x.shape
     _, Ho, Wo, _ = y.shape
-    with torch.cuda.device(x.device):
+    with _Launch("stem_conv", x.device):
         st = _lib.lib().cal_stem_conv(_dev(x, torch.float32, "stem x"), _dev(w, torch.float32, "stem w"),
                                       _dev(bias, torch.float32, "stem bias"), _dev(y, torch.float16, "stem y"),
                                       B, H, W, Ho, Wo, _stream())
@@ -118,7 +154,7 @@ def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[t
         a.src_h[i], a.src_w[i] = s.shape[1], s.shape[2]
     a.bias = _dev(bias, torch.float32, "combine bias") if bias is not None else None
     a.relu = int(relu)
-    with torch.cuda.device(y.device):
+    with _Launch("fuse_combine", y.device):
         st = _lib.lib().cal_fuse_combine(C.byref(a), _stream())
     _lib.check(st, "cal_fuse_combine")
     return y

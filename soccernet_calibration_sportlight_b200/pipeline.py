@@ -1,0 +1,61 @@
+"""The calibration hot path as one object: frames -> keypoints (-> line peaks) -> cameras.
+
+Mirrors the reference's inference driver loop body (src/utils/make_submit.py:59-73):
+``model.predict(tensor)`` followed by ``CameraCreator`` on every frame - here the camera
+solve is the batched CUDA kernel (``CameraCreator.batch``) instead of a 16-process CPU pool,
+and the optional line network (src/utils/export_line_result.py:176-185) runs in the same
+pass so its intersections can feed the solve (prediction.py:104-124) without a pickle
+round-trip.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import metamodel
+from .hrnet import w48_config
+
+
+class CalibrationPipeline:
+    """workload 'keypoints': keypoint net + decode + camera solve (what make_submit.py runs,
+    LINES_FILE=None); 'full': + line net + two-peak decode feeding line intersections."""
+
+    def __init__(self, device="cuda:0", workload: str = "keypoints", size=(540, 960),
+                 kp_state_dict=None, line_state_dict=None, camera_kwargs: Optional[dict] = None,
+                 line_sigma: float = 3.0, seed: int = 0):
+        if workload not in ("keypoints", "full"):
+            raise ValueError(workload)
+        self.device = torch.device(device)
+        self.workload = workload
+        self.size = (int(size[0]), int(size[1]))
+        self.kp_model = metamodel.HRNetMetaModel({"nn_module": {"num_refinement_stages": 0},
+                                                  "prediction_transform": {"size": self.size}})
+        if kp_state_dict is not None:
+            self.kp_model.nn_module.load_state_dict(kp_state_dict)
+        self.kp_model.set_device(self.device)
+        self.line_model = None
+        if workload == "full":
+            self.line_model = metamodel.LineMetaModel({"nn_module": {"num_refinement_stages": 0},
+                                                       "prediction_transform": {"scale": 4, "sigma": line_sigma}})
+            if line_state_dict is not None:
+                self.line_model.nn_module.load_state_dict(line_state_dict)
+            self.line_model.set_device(self.device)
+        from .prediction import CameraCreator, MAKE_SUBMIT_KWARGS
+        from .pitch import PITCH_POINTS
+        kw = dict(MAKE_SUBMIT_KWARGS if camera_kwargs is None else camera_kwargs)
+        self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
+
+    @torch.no_grad()
+    def __call__(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """frames: (B,3,H,W) fp32 in [0,1] BGR, on the host (pinned) or on the device.
+        Returns device tensors: 'keypoints' (B,57,3), optionally 'lines' (B,23,2,3), and
+        'cameras' (B,16) fp64 records (see prediction.CameraCreator.batch_records)."""
+        x = frames.to(self.device, non_blocking=True)
+        out = {"keypoints": self.kp_model.predict(x)}
+        line_pts = None
+        if self.line_model is not None:
+            out["lines"] = self.line_model.predict(x)
+            line_pts = self.camera_creator.line_points_device(out["lines"])
+        out["cameras"] = self.camera_creator.batch_records(out["keypoints"], line_pts)
+        return out

@@ -1,0 +1,42 @@
+"""One small invocation of the hot path on cuda:0, checked against the oracle
+(__graft_entry__.smoke)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def run() -> None:
+    from oracle import decode_ref, hrnet_ref
+    from tests import inputs as I
+    from . import _lib, hrnet, metamodel, ops
+
+    assert torch.cuda.is_available(), "smoke() needs a CUDA device"
+    _lib.lib()                                         # fails loudly if the .so is missing
+    dev = "cuda:0"
+    # (1) decode: bit-exact against the oracle
+    logp = I.gaussian_logp(4, 2, 58, 20, 24)
+    got = ops.kp_decode(torch.from_numpy(logp).to(dev), (40, 48)).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), decode_ref.keypoint_decode_np(logp, (40, 48)).view(np.uint32))
+    heat = I.two_peak_heat(7, 1, 23, 17, 30)
+    gl = ops.line_decode(torch.from_numpy(heat).to(dev), 3.0).cpu().numpy()
+    assert np.array_equal(gl.view(np.uint32), decode_ref.line_decode_np(heat, 3.0).view(np.uint32))
+    # (2) keypoint network + predict() on a small frame against the fp32 oracle
+    oracle = hrnet_ref.make_model("keypoints", seed=3)
+    model = metamodel.HRNetMetaModel({"nn_module": {"num_refinement_stages": 0},
+                                      "prediction_transform": {"size": (96, 160)}})
+    model.nn_module.load_state_dict(oracle.state_dict())
+    model.set_device(dev)
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(21, 1, 96, 160)))
+    with torch.no_grad():
+        ref = oracle(x)[-1]
+    out = model.nn_module(x.to(dev))[-1]
+    err = float((out.cpu() - ref).abs().max())
+    assert err <= 0.05, f"keypoint heat maps differ from the oracle by {err}"
+    pred = model.predict(x)
+    assert pred.shape == (1, 57, 3)
+    # (3) camera solve on synthetic keypoints against the oracle
+    from . import camera_smoke
+    camera_smoke.run(dev)
+    torch.cuda.synchronize()
+    print(f"smoke ok: decode bit-exact, heat-map max|err|={err:.4f}, camera solve ok")

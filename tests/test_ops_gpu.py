@@ -1,0 +1,133 @@
+"""The HRNet building kernels through the C ABI against plain PyTorch fp32 references of
+the same op on the fp16-rounded operands (isolates accumulation order; fp32 accumulate on
+tcgen05).  Tolerance: 2e-3 * max(1, |ref|_max) + 1e-3 absolute - fp16 output rounding
+(2^-11 relative) plus summation-order noise; (log)softmax outputs 2e-3 absolute."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from soccernet_calibration_sportlight_b200 import ops, packing
+
+pytestmark = pytest.mark.gpu
+dev = torch.device("cuda:0")
+
+
+def conv_case(B, H, W, ci, co, k, s, relu=True, res=False, mode=0, ncls=0, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, ci, H, W, generator=g)
+    w = torch.randn(co, ci, k, k, generator=g) * (scale / (ci * k * k) ** 0.5)
+    b = torch.randn(co, generator=g) * 0.1
+    xh = packing.to_nhwc16(x.to(dev))
+    wp, bp, rows = packing.pack_conv(w.double(), b.double())
+    Ho, Wo = (H + 2 * (k // 2) - k) // s + 1, (W + 2 * (k // 2) - k) // s + 1
+    cop = packing.pad_to(co)
+    xr = packing.from_nhwc16(xh, ci)
+    wr = w.to(torch.float16).float().to(dev)
+    ref = F.conv2d(xr, wr, b.to(dev), stride=s, padding=k // 2)
+    r16 = None
+    if res:
+        r16 = packing.to_nhwc16(torch.randn(B, co, Ho, Wo, generator=g).to(dev))
+        ref = ref + packing.from_nhwc16(r16, co)
+    if mode == 0:
+        ref = F.relu(ref) if relu else ref
+        y = torch.full((B, Ho, Wo, cop), float("nan"), dtype=torch.float16, device=dev)
+        ops.conv2d(xh, wp.to(dev), bp.to(dev), y, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16)
+        got = packing.from_nhwc16(y, co)
+        assert bool((y[..., co:] == 0).all()), "channel padding lanes must be written as zero"
+        tol = 2e-3 * max(1.0, float(ref.abs().max())) + 1e-3
+    else:
+        ref = F.log_softmax(ref, 1) if mode == 1 else F.softmax(ref, 1)
+        got = torch.full((B, ncls, Ho, Wo), float("nan"), dtype=torch.float32, device=dev)
+        ops.conv2d(xh, wp.to(dev), bp.to(dev), got, ksize=k, stride=s, cout_rows=rows, relu=False, mode=mode,
+                   n_classes=ncls)
+        tol = 2e-3
+    assert bool(torch.isfinite(got).all())
+    err = float((got - ref).abs().max())
+    assert err <= tol, f"max err {err:.3e} > tol {tol:.3e}"
+
+
+CONV_CASES = [
+    dict(B=1, H=8, W=16, ci=64, co=64, k=1, s=1),
+    dict(B=1, H=8, W=16, ci=64, co=64, k=3, s=1),
+    dict(B=2, H=9, W=20, ci=64, co=64, k=3, s=1, res=True),
+    dict(B=2, H=17, W=30, ci=48, co=48, k=3, s=1, res=True),
+    dict(B=2, H=17, W=30, ci=96, co=96, k=3, s=1, relu=False),
+    dict(B=1, H=34, W=60, ci=192, co=192, k=3, s=1, res=True),
+    dict(B=2, H=17, W=30, ci=384, co=384, k=3, s=1, res=True),
+    dict(B=1, H=20, W=24, ci=64, co=256, k=1, s=1, relu=False),
+    dict(B=1, H=20, W=24, ci=256, co=64, k=1, s=1),
+    dict(B=1, H=20, W=24, ci=256, co=48, k=3, s=1),
+    dict(B=2, H=16, W=24, ci=48, co=96, k=3, s=2),
+    dict(B=2, H=17, W=31, ci=48, co=96, k=3, s=2),
+    dict(B=1, H=135, W=240, ci=256, co=96, k=3, s=2),
+    dict(B=1, H=34, W=60, ci=192, co=384, k=3, s=2, res=True, relu=True),
+    dict(B=1, H=20, W=24, ci=384, co=48, k=1, s=1, relu=False),
+    dict(B=1, H=20, W=24, ci=64, co=784, k=1, s=1, res=True),
+    dict(B=1, H=20, W=24, ci=784, co=58, k=1, s=1, mode=1, ncls=58, scale=4.0),
+    dict(B=1, H=20, W=24, ci=720, co=23, k=1, s=1, mode=2, ncls=23, scale=4.0),
+    dict(B=3, H=135, W=240, ci=48, co=48, k=3, s=1, res=True),
+    dict(B=5, H=68, W=120, ci=96, co=96, k=3, s=1, res=True),
+    dict(B=1, H=1, W=1, ci=64, co=64, k=3, s=1),
+    dict(B=1, H=3, W=130, ci=48, co=48, k=3, s=1, res=True),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CONV_CASES)))
+def test_conv2d(case):
+    conv_case(seed=case, **CONV_CASES[case])
+
+
+def test_conv2d_rejects_bad_arguments():
+    from soccernet_calibration_sportlight_b200 import _lib
+    x = torch.zeros(1, 4, 4, 64, dtype=torch.float16, device=dev)
+    w = torch.zeros(16, 64, dtype=torch.float16, device=dev)
+    y = torch.zeros(1, 4, 4, 64, dtype=torch.float16, device=dev)
+    with pytest.raises(_lib.CalError):
+        ops.conv2d(x, w, None, y, ksize=5, stride=1, cout_rows=16, relu=False)       # weight K mismatch
+    with pytest.raises(_lib.CalError):
+        ops.conv2d(x.float(), w, None, y, ksize=1, stride=1, cout_rows=16, relu=False)  # dtype
+    y_bad = torch.zeros(1, 3, 4, 64, dtype=torch.float16, device=dev)
+    with pytest.raises(_lib.CalError):
+        ops.conv2d(x, w, None, y_bad, ksize=1, stride=1, cout_rows=16, relu=False)   # output size
+
+
+@pytest.mark.parametrize("B,H,W,Cc,srcs,relu,bias", [
+    (2, 17, 30, 48, [(17, 30), (9, 15), (5, 8)], True, False),
+    (1, 135, 240, 48, [(135, 240), (68, 120), (34, 60), (17, 30)], True, False),
+    (1, 68, 120, 96, [(68, 120), (68, 120), (34, 60), (17, 30)], True, False),
+    (1, 54, 96, 784, [(27, 48), (14, 24), (7, 12), (4, 6)], False, True),
+    (1, 1, 1, 48, [(1, 1), (1, 1)], False, False),
+])
+def test_fuse_combine(B, H, W, Cc, srcs, relu, bias):
+    g = torch.Generator().manual_seed(3)
+    cp = packing.pad_to(Cc)
+    t16 = [packing.to_nhwc16(torch.randn(B, Cc, h, w, generator=g).to(dev)) for (h, w) in srcs]
+    bvec = (torch.randn(cp, generator=g) * 0.3).to(dev) if bias else None
+    ref = torch.zeros(B, Cc, H, W, device=dev)
+    if bias:
+        ref = ref + bvec[:Cc].view(1, -1, 1, 1)
+    for t in t16:
+        tf = packing.from_nhwc16(t, Cc)
+        if tf.shape[-2:] != (H, W):
+            tf = F.interpolate(tf, size=(H, W), mode="bilinear", align_corners=True)
+        ref = ref + tf
+    ref = F.relu(ref) if relu else ref
+    y = torch.full((B, H, W, cp), float("nan"), dtype=torch.float16, device=dev)
+    ops.fuse_combine(y, t16, bvec, relu)
+    got = packing.from_nhwc16(y, Cc)
+    assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 20, 24), (2, 21, 37), (1, 540, 960)])
+def test_stem_conv(B, H, W):
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(B, 3, H, W, generator=g).to(dev)
+    w = (torch.randn(64, 3, 3, 3, generator=g) * 0.3).to(dev)
+    b = (torch.randn(64, generator=g) * 0.1).to(dev)
+    ref = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
+    Ho, Wo = ref.shape[-2:]
+    y = torch.full((B, Ho, Wo, 64), float("nan"), dtype=torch.float16, device=dev)
+    ops.stem_conv(x, w.reshape(64, 27).contiguous(), b, y)
+    got = packing.from_nhwc16(y, 64)
+    assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))

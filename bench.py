@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""Benchmark of the calibration hot path (BASELINE.json metric: calibrated frames/s at 960x540).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--impl b200|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic 960x540 frames per GPU.
+Under torchrun (N > 1) every rank processes its own shard of the batch (weak scaling) and
+one NCCL all-gather collects the per-frame results.  Rank 0 prints ONE JSON line.
+
+  value    : frames/s with the frames already resident in HBM (CUDA events, max over ranks)
+  e2e      : the same through the public API from pinned HOST frames, host->device and
+             device->host copies inside the timed region
+  roofline : the dominant kernel (tcgen05 implicit-GEMM conv) - algorithmic FLOPs of the
+             reference's convolutions / summed device time of its launches (per-launch
+             CUDA events on the launching stream, one extra profiled step) against the
+             measured bf16/fp16 tensor peak of MEASURED_PEAKS.json; the decode kernel's
+             HBM figure is reported beside it under "decode"
+  cpu_baseline : the oracle (CPU restatement of the reference) timed on this box's host
+             cores on a bounded sample (rank 0, N = 1 only)
+
+--impl reference times the reference's own CPU path (the oracle port: the Python reference
+cannot travel to the GPU box) on a bounded sample per step, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name -> (description, networks, camera solve)
+    "kp_decode": ("batch=64 HRNet-w48 keypoint forward + heatmap decode, 960x540 (BASELINE config 2)", ("keypoints",), False),
+    "keypoints": ("batch=64 HRNet-w48 keypoints + decode + camera solve, 960x540 (make_submit.py path)", ("keypoints",), True),
+    "full": ("batch=64 full pipeline: keypoint net + line net + decodes + camera solve, 960x540 (BASELINE config 3)",
+             ("keypoints", "lines"), True),
+}
+H_IMG, W_IMG = 540, 960
+BATCH_PER_GPU = 64
+METRIC = "calibrated frames/sec @960x540"
+UNIT = "frames/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor_burst=float(d["bf16_tflops"]),
+                    tensor_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms while active."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------- the reference CPU path
+class CpuPath:
+    """The oracle (CPU restatement of the reference path, oracle/): networks in fp32 through
+    torch CPU kernels, decodes, camera solve through cv2 - what prediction.py + camera.py +
+    the reference modules do on the host."""
+
+    def __init__(self, workload: str, threads: int):
+        import torch
+        from oracle import decode_ref, hrnet_ref
+        torch.set_num_threads(threads)
+        self.torch, self.decode_ref, self.hrnet_ref = torch, decode_ref, hrnet_ref
+        _, nets, solve = WORKLOADS[workload]
+        self.kp = hrnet_ref.make_model("keypoints", seed=0)
+        self.ln = hrnet_ref.make_model("lines", seed=1) if "lines" in nets else None
+        self.creator = None
+        if solve:
+            from oracle import camera_ref
+            self.camera_ref = camera_ref
+            self.creator = camera_ref.make_submit_creator()
+
+    def __call__(self, x, synth_preds=None):
+        torch = self.torch
+        with torch.no_grad():
+            preds = self.hrnet_ref.predict(self.kp, x, (H_IMG, W_IMG)).numpy()
+            line_kp = None
+            if self.ln is not None:
+                heat = self.ln(x)[-1].numpy()
+                line_kp = self.camera_ref.line_keypoints(self.decode_ref.line_transform_np(heat, scale=4, sigma=3.0))
+        cams = None
+        if self.creator is not None:
+            # random weights give conf ~ 1/58 < every threshold, so the
+            # solve is timed on synthetic keypoints of the same shape
+            src = preds if synth_preds is None else synth_preds
+            cams = [self.camera_ref.solve(self.creator, src[i], None if line_kp is None else line_kp[i])
+                    for i in range(src.shape[0])]
+        return preds, cams
+
+
+def run_reference(args, rank):
+    """--impl reference: the oracle port on the host cores, one frame per step."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from tests import inputs as I
+    cores = os.cpu_count() or 1
+    path = CpuPath(args.workload, cores)
+    frames = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, H_IMG, W_IMG)))
+    synth = synthetic_keypoints(args.steps + args.warmup, seed=5) if WORKLOADS[args.workload][2] else None
+    for i in range(args.warmup):
+        path(frames, None if synth is None else synth[i:i + 1])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        path(frames, None if synth is None else synth[args.warmup + i:args.warmup + i + 1])
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"1 frame per step x {args.steps} steps through the oracle port (torch CPU fp32 + numpy + cv2)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOADS[args.workload][0], "name": args.workload, "frames_per_step": 1},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def synthetic_keypoints(n, seed=0):
+    """(n,57,3) keypoint predictions of plausible broadcast cameras (tests/inputs.py)."""
+    from tests import camera_inputs
+    return camera_inputs.synthetic_predictions(n, seed=seed)
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from soccernet_calibration_sportlight_b200 import _lib, hrnet as P, ops
+    from soccernet_calibration_sportlight_b200.pipeline import CalibrationPipeline
+
+    _lib.lib()                                   # fail loudly if the CUDA library is missing
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    desc, nets, solve = WORKLOADS[args.workload]
+    B = args.batch
+    pipe = CalibrationPipeline(dev, workload=args.workload, size=(H_IMG, W_IMG))
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = torch.randint(0, 256, (B, 3, H_IMG, W_IMG), generator=g, dtype=torch.uint8).float().div_(255.0).pin_memory()
+    frames = host.to(dev)
+    synth = None
+    if solve:
+        # random-init weights give conf ~ 1/58 everywhere, i.e. every frame would exit the solve at
+        # the first gate; the solve therefore runs on synthetic keypoints of plausible cameras
+        # (the network's decoded keypoints are still produced and gathered)
+        synth = torch.from_numpy(synthetic_keypoints(B, seed=100 + rank)).to(dev)
+
+    def result_of(out):
+        return out["cameras"] if "cameras" in out else out["keypoints"]
+
+    gathered = None
+
+    def step(x):
+        nonlocal gathered
+        out = pipe(x, keypoints_override=synth) if solve else pipe(x)
+        res = result_of(out)
+        if world > 1:
+            if gathered is None:
+                gathered = torch.empty((world * res.shape[0],) + tuple(res.shape[1:]), dtype=res.dtype, device=dev)
+            dist.all_gather_into_tensor(gathered, res.contiguous())
+            return gathered
+        return res
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(frames)
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    n0 = ops.LAUNCHES
+    ms = timed(lambda: step(frames), args.steps)
+    launches = ops.LAUNCHES - n0
+    clocks = sampler.stop() if sampler else None
+
+    # end to end: pinned host frames -> device, pipeline, result -> host, every step
+    res_host = None
+
+    def e2e_step():
+        nonlocal res_host
+        x = host.to(dev, non_blocking=True)
+        r = step(x)
+        res_host = r.to("cpu")                   # synchronising device->host read of the result
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = host.numel() * host.element_size()
+    d2h = res_host.numel() * res_host.element_size()
+
+    # per-kernel device time: one extra step with CUDA events around every launch
+    ops.PROFILE = []
+    step(frames)
+    torch.cuda.synchronize()
+    per = {}
+    for name, a, b in ops.PROFILE:
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+    ops.PROFILE = None
+    pk = peaks()
+    conv_ms, conv_n = per.get("conv_tc", [0.0, 0])
+    gflop_frame = sum(P.conv_gflop_per_frame(k, H_IMG, W_IMG) for k in nets)
+    stem_gflop = 2.0 * 3 * 64 * 9 * 270 * 480 / 1e9 * len(nets)      # conv1 runs on CUDA cores (stem_conv)
+    conv_tflop = (gflop_frame - stem_gflop) * B / 1e3
+    achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
+    roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all conv launches of one step)", "bound": "tensor",
+            "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["tensor_sustained"], "peak_source": pk["source"] + " (sustained fp16/bf16 dense)",
+            "launches_per_step": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
+            "algorithmic_tflop_per_step": conv_tflop, "share_of_step": conv_ms / (ms / args.steps), "traffic": None}
+    dec = {}
+    if "kp_decode" in per:
+        bytes_alg = B * 57 * (H_IMG // 2) * (W_IMG // 2) * 4
+        t = per["kp_decode"][0] / 1e3
+        dec = {"kernel": "kp_decode_vec_kernel", "bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": pk["hbm"],
+               "unit": "GB/s", "frac": bytes_alg / t / 1e9 / pk["hbm"], "ms": per["kp_decode"][0]}
+    kernels_ms = {k: round(v[0], 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])}
+
+    if rank != 0:
+        return
+    frames_total = world * B * args.steps
+    line = {
+        "metric": METRIC, "value": frames_total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (tcgen05); f32 decode; f64 camera solve",
+        "data": "synthetic",
+        "config": {"workload": desc, "name": args.workload, "batch_per_gpu": B, "global_batch": world * B,
+                   "resolution": [W_IMG, H_IMG], "weights": "random-init HRNet-w48 (seeded)",
+                   "l2": "inputs larger than L2 (398 MB of frames + GBs of activations per step)",
+                   "parallelism": f"frame shards x{world}, one NCCL all-gather of the results" if world > 1 else "single GPU"},
+        "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "decode": dec, "kernels_ms_per_step": kernels_ms,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args):
+    import torch
+    from tests import inputs as I
+    cores = os.cpu_count() or 1
+    path = CpuPath(args.workload, cores)
+    n = args.cpu_frames
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, H_IMG, W_IMG)))
+    solve = WORKLOADS[args.workload][2]
+    synth = synthetic_keypoints(n + 1, seed=5) if solve else None
+    path(x, None if synth is None else synth[:1])            # warm-up frame
+    t0 = time.perf_counter()
+    for i in range(n):
+        path(x, None if synth is None else synth[i + 1:i + 2])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} frames of the same workload, batch 1, after 1 warm-up frame ({dt:.1f} s of CPU work)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("CAL_BENCH_WORKLOAD", "kp_decode"), choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -18,13 +18,14 @@ from .hrnet import w48_config
 
 
 class CalibrationPipeline:
-    """workload 'keypoints': keypoint net + decode + camera solve (what make_submit.py runs,
+    """workload 'kp_decode': keypoint net + decode only (BASELINE config 2);
+    'keypoints': keypoint net + decode + camera solve (what make_submit.py runs,
     LINES_FILE=None); 'full': + line net + two-peak decode feeding line intersections."""
 
     def __init__(self, device="cuda:0", workload: str = "keypoints", size=(540, 960),
                  kp_state_dict=None, line_state_dict=None, camera_kwargs: Optional[dict] = None,
                  line_sigma: float = 3.0, seed: int = 0):
-        if workload not in ("keypoints", "full"):
+        if workload not in ("kp_decode", "keypoints", "full"):
             raise ValueError(workload)
         self.device = torch.device(device)
         self.workload = workload
@@ -41,10 +42,12 @@ class CalibrationPipeline:
             if line_state_dict is not None:
                 self.line_model.nn_module.load_state_dict(line_state_dict)
             self.line_model.set_device(self.device)
-        from .prediction import CameraCreator, MAKE_SUBMIT_KWARGS
-        from .pitch import PITCH_POINTS
-        kw = dict(MAKE_SUBMIT_KWARGS if camera_kwargs is None else camera_kwargs)
-        self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
+        self.camera_creator = None
+        if workload != "kp_decode":
+            from .prediction import CameraCreator, MAKE_SUBMIT_KWARGS
+            from .pitch import PITCH_POINTS
+            kw = dict(MAKE_SUBMIT_KWARGS if camera_kwargs is None else camera_kwargs)
+            self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
 
     @torch.no_grad()
     def __call__(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
@@ -57,5 +60,6 @@ class CalibrationPipeline:
         if self.line_model is not None:
             out["lines"] = self.line_model.predict(x)
             line_pts = self.camera_creator.line_points_device(out["lines"])
-        out["cameras"] = self.camera_creator.batch_records(out["keypoints"], line_pts)
+        if self.camera_creator is not None:
+            out["cameras"] = self.camera_creator.batch_records(out["keypoints"], line_pts)
         return out

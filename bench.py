@@ -210,17 +210,13 @@ def run_b200(args, rank, world, local_rank):
     def result_of(out):
         return out["cameras"] if "cameras" in out else out["keypoints"]
 
-    gathered = None
+    from soccernet_calibration_sportlight_b200 import sharding
 
     def step(x):
-        nonlocal gathered
         out = pipe(x, keypoints_override=synth) if solve else pipe(x)
         res = result_of(out)
-        if world > 1:
-            if gathered is None:
-                gathered = torch.empty((world * res.shape[0],) + tuple(res.shape[1:]), dtype=res.dtype, device=dev)
-            dist.all_gather_into_tensor(gathered, res.contiguous())
-            return gathered
+        if world > 1:                             # the one collective of the path: gather the records
+            return sharding.all_gather_records(res, world * B)
         return res
 
     def barrier():
@@ -267,12 +263,21 @@ def run_b200(args, rank, world, local_rank):
     ops.PROFILE = []
     step(frames)
     torch.cuda.synchronize()
-    per = {}
+    per, by_shape = {}, {}
     for name, a, b in ops.PROFILE:
-        d = per.setdefault(name, [0.0, 0])
-        d[0] += a.elapsed_time(b)
+        t = a.elapsed_time(b)
+        d = per.setdefault(name.split(" ")[0], [0.0, 0])
+        d[0] += t
+        d[1] += 1
+        d = by_shape.setdefault(name, [0.0, 0])
+        d[0] += t
         d[1] += 1
     ops.PROFILE = None
+    if rank == 0 and args.shapes_out:
+        with open(args.shapes_out, "w") as f:
+            f.write("kernel and shape,launches,total_ms,avg_us\n")
+            for k, (t, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0]):
+                f.write(f"{k},{n},{t:.3f},{t / n * 1e3:.1f}\n")
     pk = peaks()
     conv_ms, conv_n = per.get("conv_tc", [0.0, 0])
     gflop_frame = sum(P.conv_gflop_per_frame(k, H_IMG, W_IMG) for k in nets)
@@ -337,10 +342,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("CAL_BENCH_WORKLOAD", "kp_decode"), choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=os.environ.get("CAL_BENCH_WORKLOAD", "full"), choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
-    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shapes-out", default="", help="write per-(kernel, shape) device times of one profiled step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

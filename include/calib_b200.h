@@ -118,7 +118,12 @@ int cal_fuse_combine(const CalCombineArgs* h_args, void* stream);
 
 /* ------------------------------------------------------------ camera solve -- */
 
+#define CAL_NUM_KEYPOINTS 57
+
 typedef struct CalSolveParams {
+  double pitch_xyz[CAL_NUM_KEYPOINTS * 3]; /* world coordinates (metres) of keypoint ids 0..56: the
+                         `pitch` constructor argument of CameraCreator looked up through
+                         INTERSECTON_TO_PITCH_POINTS (prediction.py:44-45, ellipse.py:99-157) */
   int32_t algorithm;  /* 0 opencv_calibration, 1 opencv_calibration_multiplane,
                          2 original_voter, 3 voter, 4 iterative_voter
                          (src/models/hrnet/prediction.py:90-96) */
@@ -135,8 +140,8 @@ typedef struct CalCameraRecord { /* 128 bytes, the all-gather payload */
   double rotation[9]; /* row-major world->camera */
   double fx, fy;
   double rmse;        /* mean reprojection L2 of the selected camera (Camera.projection_rmse) */
-  int32_t valid;      /* 0 = reference would return None */
-  int32_t branch;     /* which heuristic produced it (diagnostics) */
+  int32_t valid;      /* 0 = the reference returns None */
+  int32_t branch;     /* which heuristic produced it (solve_cascade.cuh, enum Branch) */
 } CalCameraRecord;
 
 /* Batched CameraCreator.__call__ (src/models/hrnet/prediction.py:130-136 and the
@@ -156,6 +161,17 @@ int cal_pnp_refine(const double* obj, const double* img, int n, const double* K,
                    double* rvec, double* tvec, void* stream);
 int cal_pnp_solve(const double* obj, const double* img, int n, const double* K,
                   double* rvec, double* tvec, int32_t* ok, void* stream);
+
+/* Keypoints from the line model's decoded peaks: get_line_data (src/utils/export_line_result.py:
+ * 85-131, slope/intercept per line class with both peaks at p >= prob_thre) followed by the
+ * line-pair intersections of CameraCreator.__init__ (prediction.py:110-124, 643-653), in fp32
+ * as numpy evaluates them there.
+ *   peaks    : (B, 23, 2, 3) fp32 [x, y, p], already in image pixels (cal_line_decode's scale)
+ *   pair_a/b : (57) int32 line-class channel indices whose intersection is keypoint i, -1 = none
+ *              (LINE_INTERSECTIONS, src/datatools/intersections.py:13-44)
+ *   out      : (B, 57, 2) fp64, NaN where the keypoint is not produced */
+int cal_line_points(const float* peaks, int B, int n_lines, const int32_t* pair_a, const int32_t* pair_b,
+                    float prob_thre, double* out, void* stream);
 
 /* ------------------------------------------------------------------- debug -- */
 /* Dumps the shared-memory image of one TMA box load (used by tests to pin the

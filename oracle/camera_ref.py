@@ -62,12 +62,31 @@ class CameraRef:
         self.xfocal_length = 1
         self.yfocal_length = 1
         self.principal_point = (iwidth / 2, iheight / 2)
+        # bookkeeping of this restatement only: set when solvePnPRansac reported failure, in which
+        # case the reference goes on with the UNINITIALISED rvec/tvec OpenCV hands back (it ignores
+        # the return flag, camera.py:100-103) and its result is not reproducible run to run
+        self.tainted = False
+        # ... and when solvePnPRansac was handed exactly its minimal sample size (5 points, or 4 where
+        # it switches to P3P): OpenCV then returns the minimal solver's answer directly (no RANSAC,
+        # no iterative refit); on the coplanar pitch points that answer is typically the flipped
+        # planar pose.  Deterministic, but outside what the CUDA solver restates (DESIGN.md,
+        # "parity classes").
+        self.minimal = False
+        # ... and whenever solve_pnp ran at all: even a successful solvePnPRansac seeds its answer from
+        # EPnP on random 5-point samples (OpenCV's internal RNG), and on the near-coplanar pitch
+        # points that is often the flipped planar pose, which refine_camera then keeps.
+        self.ransac = False
 
     # camera.py:92-103
     def solve_pnp(self, matches):
         obj = np.array([m[0] for m in matches])
         img = np.array([m[1] for m in matches])
-        _, rvec, t, _ = cv2.solvePnPRansac(obj, img, self.calibration, None)
+        ok, rvec, t, _ = cv2.solvePnPRansac(obj, img, self.calibration, None)
+        if not ok:
+            self.tainted = True
+        if len(matches) in (4, 5):
+            self.minimal = True
+        self.ransac = True
         self.rotation, _ = cv2.Rodrigues(rvec)
         self.position = -self.rotation.T @ t.flatten()
 
@@ -286,9 +305,15 @@ class CameraCreatorRef:
         for k, v in kwargs.items():
             setattr(self, k, v)
         self.branch = None
+        self.pinned = True      # False when the outcome depended on a tainted camera (see CameraRef)
+        self.minimal = False    # True when the outcome depended on OpenCV's 5-point EPnP shortcut
+        self.ransac = False     # True when the outcome depended on any solvePnPRansac result
 
     def __call__(self, pred, name=None):
         self.branch = None
+        self.pinned = True
+        self.minimal = False
+        self.ransac = False
         try:
             return getattr(self, self.algorithm)(pred, name)
         except Exception:
@@ -366,14 +391,21 @@ class CameraCreatorRef:
             if per_plane["groundplane"] < self.min_points_per_plane:
                 cam.solve_pnp(m)
                 self.branch = "ov_calibration+pnp"
+                self.pinned &= not cam.tainted
+                self.minimal |= cam.minimal
+                self.ransac |= cam.ransac
             if not feasible(cam.calibration, cam.position):
                 cam = None
             elif len(pts) > self.min_points_for_refinement:
                 cam.refine_camera(m)
                 self.branch += "+refine"
-        if cam is None and hom is not None and hom[1] < 26:
-            cam = hom[0]
-            self.branch = "ov_homography"
+        if cam is None and hom is not None:
+            self.pinned &= not hom[0].tainted
+            self.minimal |= hom[0].minimal
+            self.ransac |= hom[0].ransac
+            if hom[1] < 26:
+                cam = hom[0]
+                self.branch = "ov_homography"
         if cam is None:
             self.branch = None
         return cam
@@ -392,6 +424,10 @@ class CameraCreatorRef:
         cams = []
         for cand, tag in ((cand_rel, "camera_rel"), (cand_acc, "camera_acc"), (cand_all, "cam_all"),
                           (cand_gnd, "cam_ground")):
+            if cand is not None:
+                self.pinned &= not cand[0].tainted
+                self.minimal |= cand[0].minimal
+                self.ransac |= cand[0].ransac
             if cand is not None and feasible(cand[0].calibration, cand[0].position):
                 cams.append((cand[0], cand[1], tag))
         cam = None
@@ -400,9 +436,13 @@ class CameraCreatorRef:
             if best[1] < self.max_rmse:
                 cam = best[0]
                 self.branch = "voter_" + best[2]
-        if cam is None and hom is not None and hom[1] < self.max_rmse:
-            cam = hom[0]
-            self.branch = "voter_homography"
+        if cam is None and hom is not None:
+            self.pinned &= not hom[0].tainted
+            self.minimal |= hom[0].minimal
+            self.ransac |= hom[0].ransac
+            if hom[1] < self.max_rmse:
+                cam = hom[0]
+                self.branch = "voter_homography"
         return cam
 
     # prediction.py:245-257

@@ -13,6 +13,7 @@ CAL_MAX_SOURCES = 6
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_fuse_combine", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
+    "cal_line_points",
     "cal_debug_tma_probe", "cal_debug_shift_mma",
 ]
 
@@ -41,7 +42,8 @@ class CombineArgs(C.Structure):
 
 
 class SolveParams(C.Structure):
-    _fields_ = [("algorithm", C.c_int32), ("img_w", C.c_int32), ("img_h", C.c_int32),
+    _fields_ = [("pitch_xyz", C.c_double * (57 * 3)),
+                ("algorithm", C.c_int32), ("img_w", C.c_int32), ("img_h", C.c_int32),
                 ("conf_thresh", C.c_float), ("conf_threshs", C.c_float * 8),
                 ("n_conf_threshs", C.c_int32),
                 ("min_points", C.c_int32), ("min_points_per_plane", C.c_int32),
@@ -78,10 +80,10 @@ def lib() -> C.CDLL:
     L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]
     L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.cal_debug_shift_mma.argtypes = [vp, vp, i32, i32, vp, vp]
-    if hasattr(L, "cal_camera_solve"):
-        L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
-        L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
-        L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
+    L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.cal_line_points.argtypes = [vp, i32, i32, vp, vp, f32, vp, vp]
     for name in EXPORTS:
         if hasattr(L, name) and name != "cal_last_error":
             getattr(L, name).restype = C.c_int

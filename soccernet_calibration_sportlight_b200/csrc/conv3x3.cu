@@ -1,0 +1,364 @@
+// conv3x3.cu - 3x3 stride-1 convolution (+folded BN)(+residual)(+ReLU), the BasicBlock /
+// Bottleneck work-horse of HRNet (src/models/hrnet/hrnet.py:29-58, 61-99: 86 % of the conv
+// FLOPs outside the head), as an implicit GEMM on tcgen05 with a HALO tile:
+//
+//   * the input patch of a tile - (R+2) image rows x TWp = TW+2 pixels x 64 channels - is
+//     fetched ONCE per 64-channel chunk by a single 4-D TMA load (zero fill outside the image =
+//     the conv padding) and lands as (R+2)*TWp consecutive 128-byte SWIZZLE_128B rows;
+//   * the GEMM's M dimension is the flat pixel index p = r*TWp + x of that patch pitch
+//     (R*TWp = 128), so the A operand of filter tap (dy,dx) is the SAME shared-memory tile
+//     read through a descriptor whose start address is advanced by (dy*TWp + dx) rows - nine
+//     shifted views instead of nine loads (row-shifted SWIZZLE_128B descriptors are legal: the
+//     swizzle is a function of the absolute address; pinned by tools/gpu_shift_probe.py).
+//     Two of the TWp columns are halo: 6 % of the MMA rows compute values nobody stores.
+//   * weights stay resident in shared memory for the whole (persistent) CTA when they fit
+//     (C = 48 / 64), otherwise they stream through their own ring, one (tap, chunk) slice at a
+//     time;
+//   * epilogue: TMEM -> registers (32 columns per tcgen05.ld) -> bias / residual / ReLU -> fp16
+//     into a swizzled staging tile -> TMA stores (one per image row and 64-channel block; the
+//     TMA unit clips the ragged right / bottom edges), so global writes are full 128-byte lines
+//     issued by the copy engine instead of 32-byte pieces from every thread.
+//
+// L2 -> SM traffic per tile drops from 9 x 16 KB (+ all weights) to 25 KB (+ nothing when the
+// weights are resident): the old per-tap kernel ran these layers at the L2 throughput cap.
+#include "common.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int H_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int H_EPI_THREADS = 256;
+constexpr int H_MAX_A_STAGES = 4;
+constexpr int H_MAX_B_STAGES = 8;
+constexpr int H_TMEM_COLS = 512;
+constexpr int H_ACC_STRIDE = 256;
+constexpr int H_MAX_BIAS = 1024;
+constexpr int H_STAGE_BLOCK = 128 * 128;  // staging: 128 rows x 64 fp16 per channel block
+
+struct HaloParams {
+  int B, H, W, Cout_pad;
+  int TWp, TW, R;
+  int tiles_x, tiles_y, n_tiles, total_tiles;
+  int N_tile, mma_n, nblk, ncc;
+  int relu;
+  int a_stages, a_stage_bytes;
+  uint32_t a_tx_bytes;
+  int w_resident, b_stages, b_slice_bytes;
+  uint32_t b_tx_bytes;
+  const float* bias;
+  const __half* res;
+};
+
+struct HTile { int n0, b, y0, x0; };
+
+__device__ __forceinline__ HTile h_decode_tile(const HaloParams& p, int t) {
+  HTile c;
+  const int nt = t % p.n_tiles;
+  int mt = t / p.n_tiles;
+  c.n0 = nt * p.N_tile;
+  const int txi = mt % p.tiles_x;
+  mt /= p.tiles_x;
+  const int tyi = mt % p.tiles_y;
+  c.b = mt / p.tiles_y;
+  c.y0 = tyi * p.R;
+  c.x0 = txi * p.TW;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + p.a_stages * p.a_stage_bytes;
+  const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
+  uint8_t* sOut = sW + w_slots * p.b_slice_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + p.nblk * H_STAGE_BLOCK);
+  uint64_t* fullA = bars;
+  uint64_t* emptyA = fullA + H_MAX_A_STAGES;
+  uint64_t* fullB = emptyA + H_MAX_A_STAGES;
+  uint64_t* emptyB = fullB + H_MAX_B_STAGES;
+  uint64_t* wfull = emptyB + H_MAX_B_STAGES;
+  uint64_t* tfull = wfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
+    for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    mbar_init(wfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, H_TMEM_COLS);
+  for (int i = threadIdx.x; i < p.Cout_pad; i += H_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      if (p.w_resident) {
+        mbar_expect_tx(wfull, p.b_tx_bytes * 9u * static_cast<uint32_t>(p.ncc));
+        for (int s = 0; s < 9 * p.ncc; ++s) tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const HTile tc = h_decode_tile(p, t);
+        for (int cc = 0; cc < p.ncc; ++cc) {
+          mbar_wait(&emptyA[sa], pha ^ 1);
+          mbar_expect_tx(&fullA[sa], p.a_tx_bytes);
+          tma_load_4d(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+          if (!p.w_resident) {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&emptyB[sb], phb ^ 1);
+              mbar_expect_tx(&fullB[sb], p.b_tx_bytes);
+              tma_load_2d(sW + sb * p.b_slice_bytes, &tmB, &fullB[sb], (tap * p.ncc + cc) * 64, tc.n0);
+              if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int sa = 0, sb = 0, as = 0;
+      uint32_t pha = 0, phb = 0, aphase = 0;
+      const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+      if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * H_ACC_STRIDE;
+        for (int cc = 0; cc < p.ncc; ++cc) {
+          mbar_wait(&fullA[sa], pha);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(sA + sa * p.a_stage_bytes);
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - 3 * dy;
+            uint32_t b_addr;
+            if (p.w_resident) {
+              b_addr = smem_u32(sW + (tap * p.ncc + cc) * p.b_slice_bytes);
+            } else {
+              mbar_wait(&fullB[sb], phb);
+              tc_fence_after();
+              b_addr = smem_u32(sW + sb * p.b_slice_bytes);
+            }
+            const uint64_t a_desc = make_smem_desc(a_base + (dy * p.TWp + dx) * 128, 128, 2);
+            const uint64_t b_desc = make_smem_desc(b_addr, 128, 2);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (cc | tap | kk) != 0);
+            if (!p.w_resident) {
+              umma_commit(&emptyB[sb]);
+              if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            }
+          }
+          umma_commit(&emptyA[sa]);
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        }
+        umma_commit(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int groups_total = p.N_tile >> 5;                 // 32-column groups
+    const int g_split = (groups_total + 1) >> 1;
+    const int g_begin = half ? g_split : 0;
+    const int g_end = half ? groups_total : g_split;
+    const int m = quarter * 32 + lane;
+    const int r = m / p.TWp, xx = m - r * p.TWp;
+    const bool leader = (warp == 2 && lane == 0);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      const HTile tc = h_decode_tile(p, t);
+      const int y = tc.y0 + r, x = tc.x0 + xx;
+      const bool valid = (xx < p.TW) && (y < p.H) && (x < p.W);
+      const size_t pix = (static_cast<size_t>(tc.b) * p.H + y) * p.W + x;
+      const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
+      // the previous tile's TMA stores must have finished reading the staging tile
+      if (leader) bulk_wait_read();
+      named_bar_sync(1, H_EPI_THREADS);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * H_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int g = g_begin; g < g_end; ++g) {
+        uint4 rq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
+        if (rrow) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+        }
+        uint32_t acc[32];
+        if (g * 32 < p.mma_n) {
+          tmem_ld32(taddr + g * 32, acc);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0u;
+        }
+        const float* bb = s_bias + tc.n0 + g * 32;
+        uint8_t* blk = sOut + (g >> 1) * H_STAGE_BLOCK + m * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = q * 8 + 2 * j;
+            const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+            float a = (g * 32 + c < p.mma_n) ? __uint_as_float(acc[c]) : 0.0f;
+            float b = (g * 32 + c + 1 < p.mma_n) ? __uint_as_float(acc[c + 1]) : 0.0f;
+            a += bb[c] + __low2float(rh);
+            b += bb[c + 1] + __high2float(rh);
+            if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+            o[j] = h_pack_half2(a, b);
+          }
+          const int chunk = ((g & 1) * 4 + q) ^ (m & 7);       // SWIZZLE_128B: 16-byte chunk index
+          *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
+      fence_proxy_async();                                // staging writes -> visible to the TMA unit
+      named_bar_sync(1, H_EPI_THREADS);
+      if (leader) {
+        for (int kb = 0; kb < p.nblk; ++kb)
+          for (int rr = 0; rr < p.R; ++rr)
+            if (tc.y0 + rr < p.H)
+              tma_store_4d(&tmY, sOut + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, tc.y0 + rr, tc.b);
+        bulk_commit();
+      }
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (leader) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, H_TMEM_COLS);
+}
+
+}  // namespace
+
+// Chooses the tile geometry and launches; returns CAL_E_UNSUPPORTED (without setting an error
+// the caller must report) when the shape is better served by the generic kernel.
+int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
+  if (a->ksize != 3 || a->stride != 1 || a->mode != 0) return CAL_E_UNSUPPORTED;
+  HaloParams p{};
+  p.B = a->B; p.H = a->Hout; p.W = a->Wout; p.Cout_pad = a->Cout_pad;
+  // tile geometry: few tiles (MMA rows are spent on every tile, used or not) and a small halo
+  // patch (L2 -> SM bytes per tile)
+  long best = -1;
+  for (int twp = 16; twp <= 128; twp *= 2) {
+    const int tw = twp - 2, r = 128 / twp;
+    const long tiles = static_cast<long>((a->Wout + tw - 1) / tw) * ((a->Hout + r - 1) / r);
+    const long cost = tiles * (128 * 4 + (r + 2) * twp);
+    if (best < 0 || cost < best) { best = cost; p.TWp = twp; p.TW = tw; p.R = r; }
+  }
+  p.tiles_x = (a->Wout + p.TW - 1) / p.TW;
+  p.tiles_y = (a->Hout + p.R - 1) / p.R;
+  int n_tiles = 1;
+  while (a->Cout_pad % (64 * n_tiles) != 0 || a->Cout_pad / n_tiles > 256) ++n_tiles;
+  p.n_tiles = n_tiles;
+  p.N_tile = a->Cout_pad / n_tiles;
+  p.nblk = p.N_tile / 64;
+  int rows_left = a->Cout_rows;                       // weight rows available to the last N tile
+  p.mma_n = p.N_tile < rows_left ? p.N_tile : rows_left;
+  if (n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;   // ragged last N tile: generic kernel
+  p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
+  p.ncc = a->Cin_pad / 64;
+  p.relu = a->relu;
+  p.bias = a->bias;
+  p.res = reinterpret_cast<const __half*>(a->res);
+  p.a_stage_bytes = (p.R + 2) * p.TWp * 128 + 1024;   // + pad rows read by the last taps of halo columns
+  p.a_tx_bytes = static_cast<uint32_t>((p.R + 2) * p.TWp * 128);
+  p.b_slice_bytes = ((p.mma_n * 128) + 1023) & ~1023;
+  p.b_tx_bytes = static_cast<uint32_t>(p.mma_n * 128);
+  const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 5) * 8 + 16 + H_MAX_BIAS * 4;
+  const int budget = 224 * 1024 - 1024 - tail - p.nblk * H_STAGE_BLOCK;
+  const int w_all = 9 * p.ncc * p.b_slice_bytes;
+  if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget) {
+    p.w_resident = 1;
+    p.b_stages = 0;
+    p.a_stages = (budget - w_all) / p.a_stage_bytes;
+  } else {
+    p.w_resident = 0;
+    p.a_stages = 2;
+    p.b_stages = (budget - 2 * p.a_stage_bytes) / p.b_slice_bytes;
+    if (p.b_stages > H_MAX_B_STAGES) {
+      p.b_stages = H_MAX_B_STAGES;
+      p.a_stages = (budget - p.b_stages * p.b_slice_bytes) / p.a_stage_bytes;
+    }
+    if (p.b_stages < 2) return CAL_E_UNSUPPORTED;
+  }
+  if (p.a_stages > H_MAX_A_STAGES) p.a_stages = H_MAX_A_STAGES;
+  if (p.a_stages < 2) return CAL_E_UNSUPPORTED;
+  const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
+  const size_t smem = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
+                      static_cast<size_t>(w_slots) * p.b_slice_bytes + static_cast<size_t>(p.nblk) * H_STAGE_BLOCK + tail;
+
+  CUtensorMap tmA, tmB, tmY;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cin_pad, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
+    const uint64_t strides[3] = {(uint64_t)a->Cin_pad * 2, (uint64_t)a->Win * a->Cin_pad * 2,
+                                 (uint64_t)a->Hin * a->Win * a->Cin_pad * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.TWp, (uint32_t)(p.R + 2), 1};
+    int rc = encode_tmap_f16(&tmA, a->x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != CAL_OK) return rc;
+  }
+  {
+    const uint64_t ktot = 9ull * a->Cin_pad;
+    const uint64_t dims[2] = {ktot, (uint64_t)a->Cout_rows};
+    const uint64_t strides[1] = {ktot * 2};
+    const uint32_t box[2] = {64, (uint32_t)p.mma_n};
+    int rc = encode_tmap_f16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != CAL_OK) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)a->Cout_pad, (uint64_t)a->Wout, (uint64_t)a->Hout, (uint64_t)a->B};
+    const uint64_t strides[3] = {(uint64_t)a->Cout_pad * 2, (uint64_t)a->Wout * a->Cout_pad * 2,
+                                 (uint64_t)a->Hout * a->Wout * a->Cout_pad * 2};
+    const uint32_t box[4] = {64, (uint32_t)p.TW, 1, 1};
+    int rc = encode_tmap_f16(&tmY, a->y, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != CAL_OK) return rc;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CAL_CHECK_CUDA(cudaGetDevice(&dev));
+    CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv3x3_halo_kernel<<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+}  // namespace cal

@@ -19,6 +19,7 @@
 //     mbarrier ring between producer and MMA, double-buffered TMEM accumulators
 //     between MMA and epilogue so tile i+1's MMAs overlap tile i's epilogue.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -358,6 +359,14 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
     CAL_REQUIRE(a->Cout_pad == 64 && a->n_classes >= 1 && a->n_classes <= a->Cout_rows && !a->res, CAL_E_UNSUPPORTED,
                 "cal_conv2d: softmax modes need Cout_pad == 64, n_classes <= Cout_rows, no residual");
 
+  {
+    // 3x3 stride-1 layers: halo-tile kernel (conv3x3.cu); CAL_CONV_HALO=0 forces the generic one
+    static const bool use_halo = [] { const char* e = getenv("CAL_CONV_HALO"); return !(e && e[0] == '0'); }();
+    if (use_halo) {
+      const int rc = launch_conv3x3_halo(a, stream);
+      if (rc != CAL_E_UNSUPPORTED) return rc;
+    }
+  }
   ConvParams p{};
   p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout; p.Cout_pad = a->Cout_pad;
   // tile rectangle: minimise the tile count, prefer wide tiles

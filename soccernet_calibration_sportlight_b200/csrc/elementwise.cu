@@ -101,16 +101,38 @@ __device__ __forceinline__ void acc8(float* a, const uint4 q, float wgt) {
   }
 }
 
-__global__ void __launch_bounds__(256) fuse_combine_kernel(const CombineParams p) {
-  const long long total = static_cast<long long>(p.B) * p.H * p.W * p.C8;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c8 = static_cast<int>(idx % p.C8);
-    long long pix = idx / p.C8;
-    const int x = static_cast<int>(pix % p.W);
-    pix /= p.W;
-    const int y = static_cast<int>(pix % p.H);
-    const int b = static_cast<int>(pix / p.H);
+// One block row per (frame, output row): the vertical interpolation terms are block-uniform,
+// all index arithmetic is 32-bit, consecutive threads walk the channel lanes of consecutive
+// pixels (16-byte accesses, fully coalesced stores).
+constexpr int FC_THREADS = 256;
+constexpr int FC_ITEMS = 4;       // (pixel, 8-channel lane) items per thread
+
+__global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineParams p) {
+  const int row = blockIdx.x;                 // b * H + y
+  const int b = row / p.H, y = row - b * p.H;
+  const int row_items = p.W * p.C8;
+  // per-source vertical terms (uniform across the block)
+  int ys0[CAL_MAX_SOURCES], ys1[CAL_MAX_SOURCES];
+  float wy0[CAL_MAX_SOURCES], wy1[CAL_MAX_SOURCES];
+#pragma unroll
+  for (int s = 0; s < CAL_MAX_SOURCES; ++s) {
+    if (s >= p.n_src) break;
+    if (p.sh[s] == p.H && p.sw[s] == p.W) { ys0[s] = y; ys1[s] = y; wy0[s] = 1.0f; wy1[s] = 0.0f; continue; }
+    // align_corners=True source coordinates (ATen area_pixel_compute_source_index)
+    const float fy = p.scale_y[s] * static_cast<float>(y);
+    const int y0 = static_cast<int>(fy);
+    ys0[s] = y0;
+    ys1[s] = y0 + (y0 < p.sh[s] - 1 ? 1 : 0);
+    wy1[s] = fy - static_cast<float>(y0);
+    wy0[s] = 1.0f - wy1[s];
+  }
+  uint4* yrow = reinterpret_cast<uint4*>(p.y) + static_cast<size_t>(row) * row_items;
+  const int base_item = blockIdx.y * (FC_THREADS * FC_ITEMS) + threadIdx.x;
+#pragma unroll
+  for (int it = 0; it < FC_ITEMS; ++it) {
+    const int item = base_item + it * FC_THREADS;
+    if (item >= row_items) break;
+    const int x = item / p.C8, c8 = item - x * p.C8;
     float a[8];
     if (p.bias) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * c8);
@@ -127,19 +149,20 @@ __global__ void __launch_bounds__(256) fuse_combine_kernel(const CombineParams p
       const int sh = p.sh[s], sw = p.sw[s];
       const uint4* base = reinterpret_cast<const uint4*>(p.src[s]) + static_cast<size_t>(b) * sh * sw * p.C8 + c8;
       if (sh == p.H && sw == p.W) {
-        acc8(a, __ldg(base + (static_cast<size_t>(y) * sw + x) * p.C8), 1.0f);
+        acc8(a, __ldg(base + static_cast<size_t>(y * sw + x) * p.C8), 1.0f);
       } else {
-        // align_corners=True source coordinates (ATen area_pixel_compute_source_index)
-        const float fy = p.scale_y[s] * static_cast<float>(y);
         const float fx = p.scale_x[s] * static_cast<float>(x);
-        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-        const int y1 = y0 + (y0 < sh - 1 ? 1 : 0), x1 = x0 + (x0 < sw - 1 ? 1 : 0);
-        const float ly1 = fy - static_cast<float>(y0), lx1 = fx - static_cast<float>(x0);
-        const float ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
-        acc8(a, __ldg(base + (static_cast<size_t>(y0) * sw + x0) * p.C8), ly0 * lx0);
-        acc8(a, __ldg(base + (static_cast<size_t>(y0) * sw + x1) * p.C8), ly0 * lx1);
-        acc8(a, __ldg(base + (static_cast<size_t>(y1) * sw + x0) * p.C8), ly1 * lx0);
-        acc8(a, __ldg(base + (static_cast<size_t>(y1) * sw + x1) * p.C8), ly1 * lx1);
+        const int x0 = static_cast<int>(fx);
+        const int x1 = x0 + (x0 < sw - 1 ? 1 : 0);
+        const float lx1 = fx - static_cast<float>(x0), lx0 = 1.0f - lx1;
+        const uint4 q00 = __ldg(base + static_cast<size_t>(ys0[s] * sw + x0) * p.C8);
+        const uint4 q01 = __ldg(base + static_cast<size_t>(ys0[s] * sw + x1) * p.C8);
+        const uint4 q10 = __ldg(base + static_cast<size_t>(ys1[s] * sw + x0) * p.C8);
+        const uint4 q11 = __ldg(base + static_cast<size_t>(ys1[s] * sw + x1) * p.C8);
+        acc8(a, q00, wy0[s] * lx0);
+        acc8(a, q01, wy0[s] * lx1);
+        acc8(a, q10, wy1[s] * lx0);
+        acc8(a, q11, wy1[s] * lx1);
       }
     }
     uint32_t o[4];
@@ -150,7 +173,7 @@ __global__ void __launch_bounds__(256) fuse_combine_kernel(const CombineParams p
       __half2 h = __floats2half2_rn(u, v);
       o[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    reinterpret_cast<uint4*>(p.y)[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+    yrow[item] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -193,11 +216,16 @@ extern "C" int cal_fuse_combine(const CalCombineArgs* a, void* stream) {
   }
   p.bias = a->bias;
   p.relu = a->relu;
-  const long long total = static_cast<long long>(a->B) * a->H * a->W * p.C8;
-  long long blocks = (total + 255) / 256;
-  const long long cap = 148ll * 16;
-  if (blocks > cap) blocks = cap;
-  fuse_combine_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  const long long rows = static_cast<long long>(a->B) * a->H;
+  const long long row_items = static_cast<long long>(a->W) * p.C8;
+  CAL_REQUIRE(rows < (1ll << 31) && row_items < 65535ll * FC_THREADS * FC_ITEMS, CAL_E_UNSUPPORTED,
+              "cal_fuse_combine: %lld rows / %lld items per row", rows, row_items);
+  for (int i = 0; i < a->n_src; ++i)
+    CAL_REQUIRE(static_cast<long long>(a->src_h[i]) * a->src_w[i] < (1ll << 30), CAL_E_UNSUPPORTED,
+                "cal_fuse_combine: source %d too large", i);
+  const dim3 grid(static_cast<unsigned>(rows),
+                  static_cast<unsigned>((row_items + FC_THREADS * FC_ITEMS - 1) / (FC_THREADS * FC_ITEMS)));
+  fuse_combine_kernel<<<grid, FC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
 }

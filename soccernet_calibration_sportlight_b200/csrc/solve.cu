@@ -1,0 +1,162 @@
+// solve.cu - batched camera solve: one thread block per frame (CameraCreator.__call__,
+// src/models/hrnet/prediction.py:130-136 and everything it dispatches to), the two
+// single-camera helpers of the Camera mirror (baseline/camera.py:92-119) and the
+// line-intersection keypoints (prediction.py:110-124).  The arithmetic lives in
+// solve_core.cuh / solve_cascade.cuh; here are the kernels and the C ABI.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "solve_cascade.cuh"
+
+namespace cal {
+namespace {
+
+constexpr int SOLVE_THREADS = 128;
+
+__global__ void __launch_bounds__(SOLVE_THREADS) camera_solve_kernel(const float* __restrict__ preds,
+                                                                     const double* __restrict__ line_pts,
+                                                                     const __grid_constant__ CalSolveParams P,
+                                                                     CalCameraRecord* __restrict__ out) {
+  __shared__ solve::Workspace ws;
+  const solve::Team T{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)};
+  solve::Frame fr;
+  fr.pred = preds + static_cast<size_t>(blockIdx.x) * solve::NKP * 3;
+  fr.line_pts = line_pts ? line_pts + static_cast<size_t>(blockIdx.x) * solve::NKP * 2 : nullptr;
+  solve::solve_frame(T, ws, P, fr, out + blockIdx.x);
+}
+
+// mode 0: refine from (rvec, tvec); mode 1: solve from scratch (planar initialisation)
+__global__ void __launch_bounds__(SOLVE_THREADS) pnp_kernel(const double* __restrict__ obj,
+                                                            const double* __restrict__ img, int n,
+                                                            const double* __restrict__ K, double* rvec,
+                                                            double* tvec, int32_t* ok_out, int mode) {
+  __shared__ solve::Workspace ws;
+  const solve::Team T{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)};
+  if (T.tid == 0) {
+    ws.nobs = n; ws.nviews = 1; ws.use_f = 0; ws.guard = 1;
+    ws.fx = K[0]; ws.fy = K[4]; ws.cx = K[2]; ws.cy = K[5]; ws.f = K[0];
+    for (int k = 0; k < n; ++k) {
+      solve::Obs& o = ws.obs[k];
+      o.X = obj[3 * k]; o.Y = obj[3 * k + 1]; o.Z = obj[3 * k + 2];
+      o.u = img[2 * k]; o.v = img[2 * k + 1]; o.w = 1.0; o.view = 0;
+    }
+    if (mode == 0) {
+      solve::rodrigues_to_R(rvec, ws.pose[0].R);
+      for (int k = 0; k < 3; ++k) ws.pose[0].t[k] = tvec[k];
+    } else {
+      ws.hn = 0;
+      for (int k = 0; k < n && ws.hn < solve::NKP; ++k) {
+        if (fabs(obj[3 * k + 2]) > 1e-9) continue;
+        ws.hx[ws.hn] = obj[3 * k]; ws.hy[ws.hn] = obj[3 * k + 1];
+        ws.hu[ws.hn] = img[2 * k]; ws.hv[ws.hn] = img[2 * k + 1];
+        ++ws.hn;
+      }
+    }
+  }
+  T.sync();
+  bool ok = true;
+  if (mode != 0) {
+    const bool enough = ws.hn >= 4;
+    T.sync();
+    ok = enough && solve::homography_fit(T, ws, nullptr, ws.H);
+    if (T.tid == 0) ws.flag = (ok && solve::pose_from_homography(ws.H, K[0], K[4], K[2], K[5], &ws.pose[0])) ? 1 : 0;
+    T.sync();
+    ok = ws.flag != 0;
+    T.sync();
+  }
+  if (ok) solve::lm_solve(T, ws, 100);
+  if (T.tid == 0) {
+    const bool fin = ok && isfinite(ws.cost);
+    if (fin) {
+      solve::R_to_rodrigues(ws.pose[0].R, rvec);
+      for (int k = 0; k < 3; ++k) tvec[k] = ws.pose[0].t[k];
+    }
+    if (ok_out) *ok_out = fin ? 1 : 0;
+  }
+}
+
+// one thread per (frame, keypoint): fp32 arithmetic in the reference's operation order
+__global__ void line_points_kernel(const float* __restrict__ peaks, int B, int n_lines,
+                                   const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
+                                   float prob_thre, double* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * solve::NKP) return;
+  const int b = idx / solve::NKP, i = idx - b * solve::NKP;
+  double ox = CUDART_NAN, oy = CUDART_NAN;
+  const int la = pair_a[i], lb = pair_b[i];
+  if (la >= 0 && lb >= 0 && la < n_lines && lb < n_lines) {
+    float k[2], c[2];
+    bool ok = true;
+    for (int q = 0; q < 2; ++q) {
+      const float* p = peaks + (static_cast<size_t>(b) * n_lines + (q == 0 ? la : lb)) * 6;
+      // get_line_data: both peaks must pass the threshold (export_line_result.py:112-126)
+      if (!(p[2] >= prob_thre) || !(p[5] >= prob_thre)) { ok = false; break; }
+      // calculate_slope_intercept (:51-82): identical points -> no line
+      if (p[0] == p[3] && p[1] == p[4]) { ok = false; break; }
+      const float slope = __fdiv_rn(__fsub_rn(p[4], p[1]), __fadd_rn(__fsub_rn(p[3], p[0]), 0.00001f));
+      k[q] = slope;
+      c[q] = __fsub_rn(p[1], __fmul_rn(slope, p[0]));
+    }
+    // line_eq_intersection (prediction.py:643-653)
+    if (ok && fabsf(__fsub_rn(k[0], k[1])) > 1e-4f) {
+      const float x = __fdiv_rn(__fsub_rn(c[1], c[0]), __fsub_rn(k[0], k[1]));
+      const float y = __fadd_rn(__fmul_rn(k[0], x), c[0]);
+      ox = static_cast<double>(x);
+      oy = static_cast<double>(y);
+    }
+  }
+  out[2 * idx] = ox;
+  out[2 * idx + 1] = oy;
+}
+
+}  // namespace
+}  // namespace cal
+
+extern "C" int cal_camera_solve(const float* preds, const double* line_pts, const CalSolveParams* h_params,
+                                int B, CalCameraRecord* out, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(B >= 0, CAL_E_INVALID, "cal_camera_solve: B %d", B);
+  if (B == 0) return CAL_OK;
+  CAL_REQUIRE(preds && h_params && out, CAL_E_INVALID, "cal_camera_solve: null pointer");
+  CAL_REQUIRE(h_params->algorithm >= 0 && h_params->algorithm <= 4, CAL_E_INVALID, "cal_camera_solve: algorithm %d",
+              h_params->algorithm);
+  CAL_REQUIRE(h_params->n_conf_threshs >= 0 && h_params->n_conf_threshs <= 8, CAL_E_INVALID,
+              "cal_camera_solve: n_conf_threshs %d", h_params->n_conf_threshs);
+  CAL_REQUIRE(h_params->img_w > 0 && h_params->img_h > 0, CAL_E_INVALID, "cal_camera_solve: image size");
+  camera_solve_kernel<<<B, SOLVE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(preds, line_pts, *h_params, out);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_pnp_refine(const double* obj, const double* img, int n, const double* K, double* rvec,
+                              double* tvec, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(obj && img && K && rvec && tvec, CAL_E_INVALID, "cal_pnp_refine: null pointer");
+  CAL_REQUIRE(n >= 3 && n <= solve::MAXOBS, CAL_E_INVALID, "cal_pnp_refine: n %d (3..%d)", n, solve::MAXOBS);
+  pnp_kernel<<<1, SOLVE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(obj, img, n, K, rvec, tvec, nullptr, 0);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_pnp_solve(const double* obj, const double* img, int n, const double* K, double* rvec,
+                             double* tvec, int32_t* ok, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(obj && img && K && rvec && tvec, CAL_E_INVALID, "cal_pnp_solve: null pointer");
+  CAL_REQUIRE(n >= 4 && n <= solve::MAXOBS, CAL_E_INVALID, "cal_pnp_solve: n %d (4..%d)", n, solve::MAXOBS);
+  pnp_kernel<<<1, SOLVE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(obj, img, n, K, rvec, tvec, ok, 1);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_line_points(const float* peaks, int B, int n_lines, const int32_t* pair_a, const int32_t* pair_b,
+                               float prob_thre, double* out, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(B >= 0 && n_lines >= 1, CAL_E_INVALID, "cal_line_points: bad shape");
+  if (B == 0) return CAL_OK;
+  CAL_REQUIRE(peaks && pair_a && pair_b && out, CAL_E_INVALID, "cal_line_points: null pointer");
+  const int total = B * solve::NKP;
+  line_points_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(peaks, B, n_lines, pair_a,
+                                                                                       pair_b, prob_thre, out);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}

@@ -118,7 +118,8 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
     a.B, a.Hin, a.Win, a.Cin_pad = B, Hin, Win, Cin
     a.Hout, a.Wout, a.Cout_pad, a.Cout_rows = Hout, Wout, Cout_pad, cout_rows
     a.ksize, a.stride, a.relu, a.mode, a.n_classes = ksize, stride, int(relu), mode, n_classes
-    with _Launch("conv_tc", x.device):
+    name = "conv_tc" if PROFILE is None else f"conv_tc k{ksize}s{stride} {Cin}->{Cout_pad} @{Hout}x{Wout} m{mode}"
+    with _Launch(name, x.device):
         st = _lib.lib().cal_conv2d(C.byref(a), _stream())
     _lib.check(st, "cal_conv2d")
     return y
@@ -154,7 +155,8 @@ def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[t
         a.src_h[i], a.src_w[i] = s.shape[1], s.shape[2]
     a.bias = _dev(bias, torch.float32, "combine bias") if bias is not None else None
     a.relu = int(relu)
-    with _Launch("fuse_combine", y.device):
+    name = "fuse_combine" if PROFILE is None else f"fuse_combine n{len(srcs)} C{Cp} @{H}x{W}"
+    with _Launch(name, y.device):
         st = _lib.lib().cal_fuse_combine(C.byref(a), _stream())
     _lib.check(st, "cal_fuse_combine")
     return y
@@ -170,3 +172,61 @@ def tma_probe(x: torch.Tensor, box_w: int, box_h: int, estride: int, c0: int, x0
                                             estride, c0, x0, y0, n0, out.data_ptr(), _stream())
     _lib.check(st, "cal_debug_tma_probe")
     return out
+
+
+def camera_solve(preds: torch.Tensor, params: "_lib.SolveParams", line_pts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(B,57,3) fp32 keypoints [x,y,conf] (+ optional (B,57,2) fp64 line-intersection keypoints,
+    NaN = absent) -> (B,16) fp64 camera records, the 128-byte CalCameraRecord viewed as doubles:
+    position(3) rotation(9) fx fy rmse, then valid/branch packed as two int32 in the last slot
+    (prediction.py:130-136 and the algorithms it dispatches to)."""
+    if not preds.is_cuda:
+        raise _lib.CalError("camera_solve: tensor must live on a CUDA device (no CPU fallback)")
+    B = preds.shape[0]
+    if tuple(preds.shape[1:]) != (57, 3):
+        raise _lib.CalError(f"camera_solve: preds must be (B,57,3), got {tuple(preds.shape)}")
+    out = torch.zeros((B, 16), dtype=torch.float64, device=preds.device)
+    if B == 0:
+        return out
+    lp = None
+    if line_pts is not None:
+        if tuple(line_pts.shape) != (B, 57, 2):
+            raise _lib.CalError("camera_solve: line_pts must be (B,57,2)")
+        lp = _dev(line_pts, torch.float64, "camera_solve line_pts")
+    with _Launch("camera_solve", preds.device):
+        st = _lib.lib().cal_camera_solve(_dev(preds, torch.float32, "camera_solve preds"), lp, C.byref(params), B,
+                                         out.data_ptr(), _stream())
+    _lib.check(st, "cal_camera_solve")
+    return out
+
+
+def line_points(peaks: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor, prob_thre: float = 0.0) -> torch.Tensor:
+    """(B,23,2,3) decoded line peaks (image pixels) -> (B,57,2) fp64 keypoints from line
+    intersections, NaN where absent (export_line_result.py:85-131 + prediction.py:110-124)."""
+    B, n_lines = peaks.shape[0], peaks.shape[1]
+    out = torch.empty((B, 57, 2), dtype=torch.float64, device=peaks.device)
+    if B == 0:
+        return out
+    with _Launch("line_points", peaks.device):
+        st = _lib.lib().cal_line_points(_dev(peaks, torch.float32, "line_points peaks"), B, n_lines,
+                                        _dev(pair_a, torch.int32, "pair_a"), _dev(pair_b, torch.int32, "pair_b"),
+                                        float(prob_thre), out.data_ptr(), _stream())
+    _lib.check(st, "cal_line_points")
+    return out
+
+
+def pnp(obj: torch.Tensor, img: torch.Tensor, K: torch.Tensor, rvec: torch.Tensor, tvec: torch.Tensor,
+        refine: bool) -> bool:
+    """Single-camera pose: refine=True is Camera.refine_camera's solvePnPRefineLM (camera.py:105-119,
+    rvec/tvec updated in place), refine=False is Camera.solve_pnp (camera.py:92-103).  All fp64
+    device tensors: obj (n,3), img (n,2), K (3,3), rvec (3), tvec (3)."""
+    n = obj.shape[0]
+    ptrs = [_dev(t, torch.float64, "pnp") for t in (obj, img, K, rvec, tvec)]
+    with _Launch("pnp", obj.device):
+        if refine:
+            st = _lib.lib().cal_pnp_refine(ptrs[0], ptrs[1], n, ptrs[2], ptrs[3], ptrs[4], _stream())
+            ok = None
+        else:
+            ok = torch.zeros(1, dtype=torch.int32, device=obj.device)
+            st = _lib.lib().cal_pnp_solve(ptrs[0], ptrs[1], n, ptrs[2], ptrs[3], ptrs[4], ok.data_ptr(), _stream())
+    _lib.check(st, "cal_pnp")
+    return True if ok is None else bool(int(ok.item()))

@@ -50,10 +50,12 @@ class CalibrationPipeline:
             self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
 
     @torch.no_grad()
-    def __call__(self, frames: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def __call__(self, frames: torch.Tensor, keypoints_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """frames: (B,3,H,W) fp32 in [0,1] BGR, on the host (pinned) or on the device.
         Returns device tensors: 'keypoints' (B,57,3), optionally 'lines' (B,23,2,3), and
-        'cameras' (B,16) fp64 records (see prediction.CameraCreator.batch_records)."""
+        'cameras' (B,16) fp64 records (see prediction.CameraCreator.batch_records).
+        ``keypoints_override`` (B,57,3) feeds the camera solve instead of the network's own
+        keypoints (benchmarks with random-init weights, whose confidences never pass a threshold)."""
         x = frames.to(self.device, non_blocking=True)
         out = {"keypoints": self.kp_model.predict(x)}
         line_pts = None
@@ -61,5 +63,6 @@ class CalibrationPipeline:
             out["lines"] = self.line_model.predict(x)
             line_pts = self.camera_creator.line_points_device(out["lines"])
         if self.camera_creator is not None:
-            out["cameras"] = self.camera_creator.batch_records(out["keypoints"], line_pts)
+            kp = out["keypoints"] if keypoints_override is None else keypoints_override
+            out["cameras"] = self.camera_creator.batch_records(kp, line_pts)
         return out

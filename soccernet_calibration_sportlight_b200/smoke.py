@@ -35,8 +35,29 @@ def run() -> None:
     assert err <= 0.05, f"keypoint heat maps differ from the oracle by {err}"
     pred = model.predict(x)
     assert pred.shape == (1, 57, 3)
-    # (3) camera solve on synthetic keypoints against the oracle
-    from . import camera_smoke
-    camera_smoke.run(dev)
+    # (3) camera solve on synthetic keypoints against the oracle (reference heuristics on cv2)
+    from oracle import camera_ref
+    from tests import camera_inputs
+    from .pitch import PITCH_POINTS
+    from .prediction import CameraCreator
+    kps = camera_inputs.clean_predictions(6, seed=11)
+    kw = {k: v for k, v in camera_ref.MAKE_SUBMIT_KWARGS.items() if k not in ("algorithm", "conf_thresh")}
+    n_cam, worst = 0, 0.0
+    for algo in ("opencv_calibration_multiplane", "original_voter"):
+        mine = CameraCreator(PITCH_POINTS, conf_thresh=0.5, algorithm=algo, **kw)
+        ref = camera_ref.CameraCreatorRef(conf_thresh=0.5, algorithm=algo, **kw)
+        cams = mine.batch(kps)
+        for i, cam in enumerate(cams):
+            rc = ref(kps[i])
+            if not ref.pinned or ref.minimal:
+                continue                               # outcome of the reference itself not reproducible
+            assert (cam is None) == (rc is None), f"camera decision differs on frame {i} ({algo})"
+            if cam is None:
+                continue
+            n_cam += 1
+            a = np.concatenate([cam.position, cam.rotation.ravel(), [cam.xfocal_length]])
+            b = np.concatenate([rc.position, rc.rotation.ravel(), [rc.xfocal_length]])
+            worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))))
+    assert n_cam > 0 and worst < 1e-4, f"camera parameters differ from the oracle by {worst} (rel)"
     torch.cuda.synchronize()
-    print(f"smoke ok: decode bit-exact, heat-map max|err|={err:.4f}, camera solve ok")
+    print(f"smoke ok: decode bit-exact, heat-map max|err|={err:.4f}, {n_cam} cameras within {worst:.1e} of the oracle")

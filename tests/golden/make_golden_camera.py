@@ -5,9 +5,12 @@ Reference entry points run here:
   src/models/hrnet/prediction.py:44-437   CameraCreator (all five algorithms)
   baseline/camera.py:77-426               Camera
 Writes tests/golden/camera_cases.npz: the synthetic (N,57,3) keypoint sets, and per
-algorithm the reference's camera records (position, rotation, fx, fy, valid) plus the branch
-the oracle restatement took; asserts the restatement (oracle/camera_ref.py) reproduces the
-reference bit for bit on every case."""
+algorithm the reference's camera records (position, rotation, fx, fy, valid), the branch the
+oracle restatement took and a `pinned` flag.  A frame is unpinned when its outcome went through
+a cv2.solvePnPRansac call that reported failure: the reference ignores the flag and consumes
+the uninitialised rvec/tvec OpenCV returns, so ITS OWN result changes from run to run there.
+Asserts the restatement (oracle/camera_ref.py) reproduces the reference bit for bit on every
+pinned frame."""
 import os
 import sys
 
@@ -44,7 +47,7 @@ for sname, preds in sets.items():
         ref = CameraCreator(PITCH_POINTS, conf_thresh=thr, algorithm=algo, **KW)
         mine = O.CameraCreatorRef(conf_thresh=thr, algorithm=algo, **KW)
         recs = np.zeros((preds.shape[0], 16))
-        branches = []
+        branches, pinned, minimal, ransac = [], [], [], []
         for i in range(preds.shape[0]):
             with refimport.quiet():
                 c_ref = ref(preds[i], f"{sname}_{i}")
@@ -53,6 +56,12 @@ for sname, preds in sets.items():
             r2 = O.camera_record(c_mine)
             same = np.array_equal(recs[i], r2) or (np.isnan(recs[i]).any() and np.array_equal(
                 np.isnan(recs[i]), np.isnan(r2)))
+            pinned.append(bool(mine.pinned))
+            minimal.append(bool(mine.minimal))
+            ransac.append(bool(mine.ransac))
+            if not mine.pinned:
+                branches.append((mine.branch or "none") + "!")
+                continue
             assert same, (sname, algo, i, recs[i], r2)
             if c_ref is not None:
                 j1, j2 = c_ref.to_json_parameters(), c_mine.to_json_parameters()
@@ -61,6 +70,9 @@ for sname, preds in sets.items():
             branches.append(mine.branch or "none")
         out[f"{sname}__{algo}__records"] = recs
         out[f"{sname}__{algo}__branch"] = np.array(branches)
+        out[f"{sname}__{algo}__pinned"] = np.array(pinned)
+        out[f"{sname}__{algo}__minimal"] = np.array(minimal)
+        out[f"{sname}__{algo}__ransac"] = np.array(ransac)
         uniq, cnt = np.unique(branches, return_counts=True)
         lines.append(f"{sname:7s} {algo:30s} n={preds.shape[0]} " + " ".join(f"{u}:{c}" for u, c in zip(uniq, cnt)))
 np.savez_compressed(os.path.join(HERE, "camera_cases.npz"), **out)

@@ -2,17 +2,20 @@
 # One GPU-box visit: parity tests, bench line, ncu launch list, ncu --set full captures.
 # usage (under gpurun): bash tools/gpu_round.sh [tag] [workload]
 TAG=${1:-r1}
-WL=${2:-kp_decode}
+WL=${2:-full}
+NCU=${3:-1}
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.txt 2>&1
 nproc > $OUT/${TAG}_nproc.txt
 timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest_gpu.log
 tail -3 $OUT/${TAG}_pytest_gpu.log
-timeout 900 python bench.py --workload $WL --steps 10 --warmup 3 > $OUT/${TAG}_bench_${WL}.json 2> $OUT/${TAG}_bench_${WL}.err; echo "bench rc=$?"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $OUT/${TAG}_smoke.log
+timeout 900 python bench.py --workload $WL --steps 10 --warmup 3 --shapes-out $OUT/${TAG}_shapes_${WL}.csv > $OUT/${TAG}_bench_${WL}.json 2> $OUT/${TAG}_bench_${WL}.err; echo "bench rc=$?"
 cat $OUT/${TAG}_bench_${WL}.json
 timeout 600 python bench.py --workload $WL --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_${WL}_ref.json 2>> $OUT/${TAG}_bench_${WL}.err
 cat $OUT/${TAG}_bench_${WL}_ref.json
+if [ "$NCU" = "1" ]; then
 # launch list of the bench command (shares of the step; numbers printed under ncu are not bench values)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/${TAG}_launches_${WL}.csv \
     python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_under_ncu.txt 2>&1
@@ -21,4 +24,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv
     python tools/ncu_forward.py 64 keypoints > $OUT/${TAG}_ncu_conv.txt 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:kp_decode -s 1 -c 1 -f -o $OUT/${TAG}_decode \
     python tools/ncu_forward.py 64 keypoints > $OUT/${TAG}_ncu_decode.txt 2>&1
-ls -la $OUT
+fi
+ls -la $OUT | tail -20

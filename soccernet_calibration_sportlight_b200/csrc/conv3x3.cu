@@ -41,7 +41,7 @@ struct HaloParams {
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int N_tile, mma_n, nblk, ncc;
   int relu;
-  int a_stages, a_stage_bytes;
+  int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
   int w_resident, b_stages, b_slice_bytes;
   uint32_t b_tx_bytes;
@@ -70,6 +70,7 @@ __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <bool RESIDENT>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
@@ -77,9 +78,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = sA + p.a_stages * p.a_stage_bytes;
-  const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
+  const int w_slots = RESIDENT ? 9 * p.ncc : p.b_stages;
   uint8_t* sOut = sW + w_slots * p.b_slice_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + p.nblk * H_STAGE_BLOCK);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + p.out_bufs * p.nblk * H_STAGE_BLOCK);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + H_MAX_A_STAGES;
   uint64_t* fullB = emptyA + H_MAX_A_STAGES;
@@ -99,7 +100,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(wfull, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, H_TMEM_COLS);
@@ -112,7 +113,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      if (p.w_resident) {
+      if (RESIDENT) {
         mbar_expect_tx(wfull, p.b_tx_bytes * 9u * static_cast<uint32_t>(p.ncc));
         for (int s = 0; s < 9 * p.ncc; ++s) tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
       }
@@ -125,7 +126,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_expect_tx(&fullA[sa], p.a_tx_bytes);
           tma_load_4d(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
-          if (!p.w_resident) {
+          if (!RESIDENT) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&emptyB[sb], phb ^ 1);
               mbar_expect_tx(&fullB[sb], p.b_tx_bytes);
@@ -138,79 +139,109 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int sa = 0, sb = 0, as = 0;
-      uint32_t pha = 0, phb = 0, aphase = 0;
-      const uint32_t idesc = make_idesc_f16(128, p.mma_n);
-      if (p.w_resident) { mbar_wait(wfull, 0); tc_fence_after(); }
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * H_ACC_STRIDE;
-        for (int cc = 0; cc < p.ncc; ++cc) {
-          mbar_wait(&fullA[sa], pha);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + sa * p.a_stage_bytes);
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - 3 * dy;
-            uint32_t b_addr;
-            if (p.w_resident) {
-              b_addr = smem_u32(sW + (tap * p.ncc + cc) * p.b_slice_bytes);
-            } else {
-              mbar_wait(&fullB[sb], phb);
-              tc_fence_after();
-              b_addr = smem_u32(sW + sb * p.b_slice_bytes);
-            }
-            const uint64_t a_desc = make_smem_desc(a_base + (dy * p.TWp + dx) * 128, 128, 2);
-            const uint64_t b_desc = make_smem_desc(b_addr, 128, 2);
+    // The whole warp walks the (warp-uniform) schedule and one elected lane issues, so the
+    // descriptors live in uniform registers; per MMA only a 32-bit add on the descriptor's
+    // address field remains (N is 48..192 here: an MMA retires every 24..96 cycles, so the
+    // issue loop has to be a handful of instructions per MMA).
+    int sa = 0, sb = 0, as = 0;
+    uint32_t pha = 0, phb = 0, aphase = 0;
+    const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+    const uint64_t desc0 = make_smem_desc(0, 128, 2);      // everything but the start address
+    uint32_t tap_off[9];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (cc | tap | kk) != 0);
-            if (!p.w_resident) {
-              umma_commit(&emptyB[sb]);
-              if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
-            }
+    for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(((tap / 3) * p.TWp + (tap % 3)) * 128) >> 4;
+    const bool issuer = elect_one();
+    if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
+    const uint32_t w0 = (smem_u32(sW) & 0x3FFFF) >> 4, w_tap = static_cast<uint32_t>(p.ncc * p.b_slice_bytes) >> 4,
+                   w_cc = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * H_ACC_STRIDE;
+      for (int cc = 0; cc < p.ncc; ++cc) {
+        mbar_wait(&fullA[sa], pha);
+        tc_fence_after();
+        const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + sa * p.a_stage_bytes) & 0x3FFFF) >> 4);
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          uint64_t b0;
+          if (RESIDENT) {
+            b0 = desc0 | static_cast<uint64_t>(w0 + tap * w_tap + cc * w_cc);
+          } else {
+            mbar_wait(&fullB[sb], phb);
+            tc_fence_after();
+            b0 = desc0 | static_cast<uint64_t>((smem_u32(sW + sb * p.b_slice_bytes) & 0x3FFFF) >> 4);
           }
-          umma_commit(&emptyA[sa]);
-          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+          if (issuer) {
+            const uint64_t at = a0 + tap_off[tap];
+            umma_f16(d_tmem, at, b0, idesc, (cc | tap) != 0);
+            umma_f16(d_tmem, at + 2, b0 + 2, idesc, 1);
+            umma_f16(d_tmem, at + 4, b0 + 4, idesc, 1);
+            umma_f16(d_tmem, at + 6, b0 + 6, idesc, 1);
+            if (!RESIDENT) umma_commit(&emptyB[sb]);
+          }
+          __syncwarp();
+          if (!RESIDENT) {
+            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+          }
         }
-        umma_commit(&tfull[as]);
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        if (issuer) umma_commit(&emptyA[sa]);
+        __syncwarp();
+        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
       }
+      if (issuer) umma_commit(&tfull[as]);
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    // Two groups of four warps ping-pong over the tiles: group g owns TMEM accumulator stage g
+    // and staging buffer g, so the latency chain of one tile's epilogue (TMEM load, residual
+    // read, staging, store issue) overlaps the other group's.
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;
     const int groups_total = p.N_tile >> 5;                 // 32-column groups
-    const int g_split = (groups_total + 1) >> 1;
-    const int g_begin = half ? g_split : 0;
-    const int g_end = half ? groups_total : g_split;
     const int m = quarter * 32 + lane;
     const int r = m / p.TWp, xx = m - r * p.TWp;
-    const bool leader = (warp == 2 && lane == 0);
-    int as = 0;
+    const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
+    uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
+    const bool prefetch_res = (p.res != nullptr) && groups_total <= 2;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const HTile tc = h_decode_tile(p, t);
       const int y = tc.y0 + r, x = tc.x0 + xx;
       const bool valid = (xx < p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tc.b) * p.H + y) * p.W + x;
       const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
-      // the previous tile's TMA stores must have finished reading the staging tile
+      uint4 rpre[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rpre[q] = make_uint4(0, 0, 0, 0);
+      if (prefetch_res && rrow) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < groups_total * 4) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
+      }
+      // this group's previous TMA stores must have finished reading its staging buffer
       if (leader) bulk_wait_read();
-      named_bar_sync(1, H_EPI_THREADS);
-      mbar_wait(&tfull[as], aphase);
+      named_bar_sync(1 + grp, 128);
+      mbar_wait(&tfull[grp], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * H_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int g = g_begin; g < g_end; ++g) {
+      const uint32_t taddr = tmem_base + grp * H_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int g = 0; g < groups_total; ++g) {
         uint4 rq[4];
+        if (prefetch_res) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
-        if (rrow) {
+          for (int q = 0; q < 4; ++q) rq[q] = (g == 0) ? rpre[q] : rpre[4 + q];
+        } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+          for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
+          if (rrow) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+          }
         }
         uint32_t acc[32];
         if (g * 32 < p.mma_n) {
@@ -221,7 +252,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; ++j) acc[j] = 0u;
         }
         const float* bb = s_bias + tc.n0 + g * 32;
-        uint8_t* blk = sOut + (g >> 1) * H_STAGE_BLOCK + m * 128;
+        uint8_t* blk = sStage + (g >> 1) * H_STAGE_BLOCK + m * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
@@ -243,18 +274,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
+      if (lane == 0) mbar_arrive(&tempty[grp]);           // accumulator drained
       fence_proxy_async();                                // staging writes -> visible to the TMA unit
-      named_bar_sync(1, H_EPI_THREADS);
+      named_bar_sync(1 + grp, 128);
       if (leader) {
         for (int kb = 0; kb < p.nblk; ++kb)
           for (int rr = 0; rr < p.R; ++rr)
             if (tc.y0 + rr < p.H)
-              tma_store_4d(&tmY, sOut + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, tc.y0 + rr, tc.b);
+              tma_store_4d(&tmY, sStage + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, tc.y0 + rr, tc.b);
         bulk_commit();
       }
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      aphase ^= 1;
     }
     if (leader) bulk_wait_all();
   }
@@ -301,8 +331,10 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   p.b_slice_bytes = ((p.mma_n * 128) + 1023) & ~1023;
   p.b_tx_bytes = static_cast<uint32_t>(p.mma_n * 128);
   const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 5) * 8 + 16 + H_MAX_BIAS * 4;
-  const int budget = 224 * 1024 - 1024 - tail - p.nblk * H_STAGE_BLOCK;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
+  // one staging buffer per epilogue group
+  p.out_bufs = 2;
+  const int budget = 224 * 1024 - 1024 - tail - 2 * p.nblk * H_STAGE_BLOCK;
   if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget) {
     p.w_resident = 1;
     p.b_stages = 0;
@@ -321,7 +353,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   if (p.a_stages < 2) return CAL_E_UNSUPPORTED;
   const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
   const size_t smem = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
-                      static_cast<size_t>(w_slots) * p.b_slice_bytes + static_cast<size_t>(p.nblk) * H_STAGE_BLOCK + tail;
+                      static_cast<size_t>(w_slots) * p.b_slice_bytes + static_cast<size_t>(p.out_bufs) * p.nblk * H_STAGE_BLOCK + tail;
 
   CUtensorMap tmA, tmB, tmY;
   {
@@ -353,10 +385,14 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     int dev = 0;
     CAL_CHECK_CUDA(cudaGetDevice(&dev));
     CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv3x3_halo_kernel<<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
+  if (p.w_resident)
+    conv3x3_halo_kernel<true><<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
+  else
+    conv3x3_halo_kernel<false><<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
 }

@@ -124,31 +124,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int stage = 0, as = 0;
-      uint32_t phase = 0, aphase = 0;
-      const uint32_t idesc = make_idesc_f16(128, p.mma_n);
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        mbar_wait(&tempty[as], aphase ^ 1);
+    // warp-uniform schedule, one elected lane issues: descriptors stay in uniform registers
+    int stage = 0, as = 0;
+    uint32_t phase = 0, aphase = 0;
+    const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+    const uint64_t desc0 = make_smem_desc(0, 128, 2);
+    const bool issuer = elect_one();
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      for (int k = 0; k < p.num_k; ++k) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-        for (int k = 0; k < p.num_k; ++k) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * A_STAGE_BYTES), 128, 2);
-          const uint64_t b_desc = make_smem_desc(smem_u32(sB + stage * p.b_stage_bytes), 128, 2);
-#pragma unroll
-          for (int kk = 0; kk < KC / 16; ++kk) {
-            // +32 bytes per K=16 step inside the 128-byte swizzle span
-            umma_f16(d_tmem, a_desc + 2 * kk, b_desc + 2 * kk, idesc, (k | kk) != 0);
-          }
+        const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + stage * A_STAGE_BYTES) & 0x3FFFF) >> 4);
+        const uint64_t b0 = desc0 | static_cast<uint64_t>((smem_u32(sB + stage * p.b_stage_bytes) & 0x3FFFF) >> 4);
+        if (issuer) {
+          // +32 bytes per K=16 step inside the 128-byte swizzle span
+          umma_f16(d_tmem, a0, b0, idesc, k != 0);
+          umma_f16(d_tmem, a0 + 2, b0 + 2, idesc, 1);
+          umma_f16(d_tmem, a0 + 4, b0 + 4, idesc, 1);
+          umma_f16(d_tmem, a0 + 6, b0 + 6, idesc, 1);
           umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull[as]);        // accumulator complete -> epilogue
-        as ^= 1;
-        if (as == 0) aphase ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (issuer) umma_commit(&tfull[as]);        // accumulator complete -> epilogue
+      __syncwarp();
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
     }
   } else {
     // ---------------------------------------------------------------- epilogue

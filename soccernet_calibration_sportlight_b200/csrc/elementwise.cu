@@ -101,38 +101,25 @@ __device__ __forceinline__ void acc8(float* a, const uint4 q, float wgt) {
   }
 }
 
-// One block row per (frame, output row): the vertical interpolation terms are block-uniform,
-// all index arithmetic is 32-bit, consecutive threads walk the channel lanes of consecutive
-// pixels (16-byte accesses, fully coalesced stores).
+// One block per (frame, FC_TY x FC_TX output patch, all channel lanes): the bilinear footprint of
+// the patch in every source (a few KB to ~100 KB) stays in L1 while the block walks the patch,
+// so each source line crosses the L2 -> SM fabric about once instead of once per output that
+// touches it (a row-wise version of this kernel ran at the L2 throughput cap: 16 gathers per
+// output).  Consecutive threads take consecutive 8-channel lanes of one pixel (16-byte,
+// coalesced); all index arithmetic is 32-bit.
 constexpr int FC_THREADS = 256;
-constexpr int FC_ITEMS = 4;       // (pixel, 8-channel lane) items per thread
+constexpr int FC_TY = 8, FC_TX = 16;
 
 __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineParams p) {
-  const int row = blockIdx.x;                 // b * H + y
-  const int b = row / p.H, y = row - b * p.H;
-  const int row_items = p.W * p.C8;
-  // per-source vertical terms (uniform across the block)
-  int ys0[CAL_MAX_SOURCES], ys1[CAL_MAX_SOURCES];
-  float wy0[CAL_MAX_SOURCES], wy1[CAL_MAX_SOURCES];
-#pragma unroll
-  for (int s = 0; s < CAL_MAX_SOURCES; ++s) {
-    if (s >= p.n_src) break;
-    if (p.sh[s] == p.H && p.sw[s] == p.W) { ys0[s] = y; ys1[s] = y; wy0[s] = 1.0f; wy1[s] = 0.0f; continue; }
-    // align_corners=True source coordinates (ATen area_pixel_compute_source_index)
-    const float fy = p.scale_y[s] * static_cast<float>(y);
-    const int y0 = static_cast<int>(fy);
-    ys0[s] = y0;
-    ys1[s] = y0 + (y0 < p.sh[s] - 1 ? 1 : 0);
-    wy1[s] = fy - static_cast<float>(y0);
-    wy0[s] = 1.0f - wy1[s];
-  }
-  uint4* yrow = reinterpret_cast<uint4*>(p.y) + static_cast<size_t>(row) * row_items;
-  const int base_item = blockIdx.y * (FC_THREADS * FC_ITEMS) + threadIdx.x;
-#pragma unroll
-  for (int it = 0; it < FC_ITEMS; ++it) {
-    const int item = base_item + it * FC_THREADS;
-    if (item >= row_items) break;
-    const int x = item / p.C8, c8 = item - x * p.C8;
+  const int b = blockIdx.z;
+  const int y_base = blockIdx.y * FC_TY, x_base = blockIdx.x * FC_TX;
+  const int tx_n = min(FC_TX, p.W - x_base), ty_n = min(FC_TY, p.H - y_base);
+  const int row_items = tx_n * p.C8;
+  const int items = ty_n * row_items;
+  for (int item = threadIdx.x; item < items; item += FC_THREADS) {
+    const int py = item / row_items, rem = item - py * row_items;
+    const int px = rem / p.C8, c8 = rem - px * p.C8;
+    const int y = y_base + py, x = x_base + px;
     float a[8];
     if (p.bias) {
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias) + 2 * c8);
@@ -151,18 +138,21 @@ __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineP
       if (sh == p.H && sw == p.W) {
         acc8(a, __ldg(base + static_cast<size_t>(y * sw + x) * p.C8), 1.0f);
       } else {
+        // align_corners=True source coordinates (ATen area_pixel_compute_source_index)
+        const float fy = p.scale_y[s] * static_cast<float>(y);
         const float fx = p.scale_x[s] * static_cast<float>(x);
-        const int x0 = static_cast<int>(fx);
-        const int x1 = x0 + (x0 < sw - 1 ? 1 : 0);
-        const float lx1 = fx - static_cast<float>(x0), lx0 = 1.0f - lx1;
-        const uint4 q00 = __ldg(base + static_cast<size_t>(ys0[s] * sw + x0) * p.C8);
-        const uint4 q01 = __ldg(base + static_cast<size_t>(ys0[s] * sw + x1) * p.C8);
-        const uint4 q10 = __ldg(base + static_cast<size_t>(ys1[s] * sw + x0) * p.C8);
-        const uint4 q11 = __ldg(base + static_cast<size_t>(ys1[s] * sw + x1) * p.C8);
-        acc8(a, q00, wy0[s] * lx0);
-        acc8(a, q01, wy0[s] * lx1);
-        acc8(a, q10, wy1[s] * lx0);
-        acc8(a, q11, wy1[s] * lx1);
+        const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+        const int y1 = y0 + (y0 < sh - 1 ? 1 : 0), x1 = x0 + (x0 < sw - 1 ? 1 : 0);
+        const float ly1 = fy - static_cast<float>(y0), lx1 = fx - static_cast<float>(x0);
+        const float ly0 = 1.0f - ly1, lx0 = 1.0f - lx1;
+        const uint4 q00 = __ldg(base + static_cast<size_t>(y0 * sw + x0) * p.C8);
+        const uint4 q01 = __ldg(base + static_cast<size_t>(y0 * sw + x1) * p.C8);
+        const uint4 q10 = __ldg(base + static_cast<size_t>(y1 * sw + x0) * p.C8);
+        const uint4 q11 = __ldg(base + static_cast<size_t>(y1 * sw + x1) * p.C8);
+        acc8(a, q00, ly0 * lx0);
+        acc8(a, q01, ly0 * lx1);
+        acc8(a, q10, ly1 * lx0);
+        acc8(a, q11, ly1 * lx1);
       }
     }
     uint32_t o[4];
@@ -173,7 +163,8 @@ __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineP
       __half2 h = __floats2half2_rn(u, v);
       o[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    yrow[item] = make_uint4(o[0], o[1], o[2], o[3]);
+    reinterpret_cast<uint4*>(p.y)[(static_cast<size_t>(b) * p.H + y) * p.W * p.C8 + static_cast<size_t>(x) * p.C8 + c8] =
+        make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -216,15 +207,14 @@ extern "C" int cal_fuse_combine(const CalCombineArgs* a, void* stream) {
   }
   p.bias = a->bias;
   p.relu = a->relu;
-  const long long rows = static_cast<long long>(a->B) * a->H;
-  const long long row_items = static_cast<long long>(a->W) * p.C8;
-  CAL_REQUIRE(rows < (1ll << 31) && row_items < 65535ll * FC_THREADS * FC_ITEMS, CAL_E_UNSUPPORTED,
-              "cal_fuse_combine: %lld rows / %lld items per row", rows, row_items);
+  CAL_REQUIRE(a->B <= 65535 && (a->H + FC_TY - 1) / FC_TY <= 65535 &&
+                  static_cast<long long>(a->H) * a->W < (1ll << 30),
+              CAL_E_UNSUPPORTED, "cal_fuse_combine: tensor too large");
   for (int i = 0; i < a->n_src; ++i)
     CAL_REQUIRE(static_cast<long long>(a->src_h[i]) * a->src_w[i] < (1ll << 30), CAL_E_UNSUPPORTED,
                 "cal_fuse_combine: source %d too large", i);
-  const dim3 grid(static_cast<unsigned>(rows),
-                  static_cast<unsigned>((row_items + FC_THREADS * FC_ITEMS - 1) / (FC_THREADS * FC_ITEMS)));
+  const dim3 grid(static_cast<unsigned>((a->W + FC_TX - 1) / FC_TX), static_cast<unsigned>((a->H + FC_TY - 1) / FC_TY),
+                  static_cast<unsigned>(a->B));
   fuse_combine_kernel<<<grid, FC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;

@@ -116,6 +116,29 @@ typedef struct CalCombineArgs {
  * bilinear interpolation. */
 int cal_fuse_combine(const CalCombineArgs* h_args, void* stream);
 
+#define CAL_MAX_LOW 4
+typedef struct CalHeadArgs {
+  const void* full;      /* fp16 NHWC (B, H, W, 64): the full-resolution source of the head (x_stem for the
+                            keypoint net, branch 0 for the line net), channels padded to 64 */
+  const void* w_full;    /* fp16 (Cout_rows, 64) K-major: the columns of the first head conv that multiply
+                            `full`, BN folded */
+  const void* low[CAL_MAX_LOW];  /* fp16 NHWC (B, h_i, w_i, Cout_pad): p_i = W1_i * y_i, the same conv applied
+                            to every lower-resolution branch at ITS resolution (no bias) */
+  int32_t low_h[CAL_MAX_LOW], low_w[CAL_MAX_LOW];
+  int32_t n_low;
+  const float* bias;     /* fp32 (Cout_pad): conv bias with BN folded */
+  void* z;               /* fp16 NHWC (B, H, W, Cout_pad) */
+  int32_t B, H, W, Cf_pad, Cout_pad, Cout_rows;
+} CalHeadArgs;
+
+/* z = ReLU( W1_full * full + sum_i bilinear_up(p_i) + bias ): the upsample + concat + first 1x1 conv
+ * + BN + ReLU of the head (src/models/hrnet/hrnet.py:489-511 with last_layer[0:3] :316-324;
+ * src/models/line/hrnet.py:236-249) as one tensor-core accumulation per tile, the bilinear
+ * interpolation (align_corners=True) expressed as a small GEMM against the source patches.
+ * Returns CAL_E_UNSUPPORTED when a source's footprint does not fit (caller falls back to
+ * cal_fuse_combine + cal_conv2d). */
+int cal_head_fused(const CalHeadArgs* h_args, void* stream);
+
 /* ------------------------------------------------------------ camera solve -- */
 
 #define CAL_NUM_KEYPOINTS 57
@@ -185,6 +208,11 @@ int cal_debug_tma_probe(const void* x, int B, int H, int W, int C, int box_w, in
  * D(128x64 fp32) = X[shift : shift+128, :] * W^T with X (256,64), W (64,64) fp16. */
 int cal_debug_shift_mma(const void* x_256x64, const void* w_64x64, int shift,
                         int base_offset_mode, float* out_128x64, void* stream);
+
+/* Experiment pinning the MN-major (N contiguous) B-operand descriptor convention used by the
+ * fused head's interpolation GEMM: D(128x128 fp32) = X(128x64) * Y(64x128), Y row-major. */
+int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int mode, float* out_128x128,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,9 +12,9 @@ CAL_MAX_SOURCES = 6
 
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
-    "cal_stem_conv", "cal_fuse_combine", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
+    "cal_stem_conv", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points",
-    "cal_debug_tma_probe", "cal_debug_shift_mma",
+    "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma",
 ]
 
 
@@ -39,6 +39,14 @@ class CombineArgs(C.Structure):
                 ("src_h", C.c_int32 * CAL_MAX_SOURCES),
                 ("src_w", C.c_int32 * CAL_MAX_SOURCES),
                 ("bias", C.c_void_p), ("relu", C.c_int32)]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("full", C.c_void_p), ("w_full", C.c_void_p), ("low", C.c_void_p * 4),
+                ("low_h", C.c_int32 * 4), ("low_w", C.c_int32 * 4), ("n_low", C.c_int32),
+                ("bias", C.c_void_p), ("z", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cf_pad", C.c_int32),
+                ("Cout_pad", C.c_int32), ("Cout_rows", C.c_int32)]
 
 
 class SolveParams(C.Structure):
@@ -78,8 +86,10 @@ def lib() -> C.CDLL:
     L.cal_conv2d.argtypes = [C.POINTER(ConvArgs), vp]
     L.cal_stem_conv.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]
+    L.cal_head_fused.argtypes = [C.POINTER(HeadArgs), vp]
     L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.cal_debug_shift_mma.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.cal_debug_mn_mma.argtypes = [vp, vp, i32, vp, vp]
     L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
     L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]

@@ -192,6 +192,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // K-major operand tile, rows of KC fp16 (KC*2 bytes == swizzle span), 8-row groups
 // contiguous: the canonical layout TMA writes for a (KC, rows) box.
 //   layout_type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B (cute/arch/mma_sm100_desc.hpp)
+// general form: explicit leading / stride byte offsets (MN-major operands need both)
+__device__ __forceinline__ uint64_t make_smem_desc_ex(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t row_bytes,
                                                    uint32_t layout_type) {
   uint64_t d = 0;

@@ -329,6 +329,55 @@ __global__ void shift_mma_probe_kernel(const __grid_constant__ CUtensorMap tmX,
   if (warp == 0) tmem_dealloc(tmem_base, 64);
 }
 
+// Experiment: MN-major B operand (N contiguous, the layout of an NHWC activation tile used as
+// the "weights" of an interpolation GEMM).  D(128x128) = X(128x64, K-major) * Y(64x128, N contiguous).
+__global__ void mn_mma_probe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                                    int mode, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 128 x 128 B
+  uint8_t* sB = smem + 128 * 128;     // 2 blocks of [64 K-rows][64 N-elements]
+  __shared__ uint64_t bar, mbar;
+  __shared__ uint32_t tslot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&mbar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tslot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tslot;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 128 * 128 + 2 * 64 * 128);
+    tma_load_2d(sA, &tmX, &bar, 0, 0);
+    tma_load_2d(sB, &tmY, &bar, 0, 0);
+    tma_load_2d(sB + 8192, &tmY, &bar, 64, 0);
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lbo = (mode & 1) ? 1024 : 8192, sbo = (mode & 1) ? 8192 : 1024;
+    const uint32_t idesc = make_idesc_f16(128, 128) | (1u << 16);     // B is MN-major
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint64_t a_desc = make_smem_desc(smem_u32(sA), 128, 2) + 2 * kk;
+      const uint64_t b_desc = make_smem_desc_ex(smem_u32(sB) + kk * 16 * 128, lbo, sbo, 2);
+      umma_f16(tmem_base, a_desc, b_desc, idesc, kk != 0);
+    }
+    umma_commit(&mbar);
+  }
+  mbar_wait(&mbar, 0);
+  tc_fence_after();
+  if (warp < 4) {
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int g = 0; g < 8; ++g) {
+      uint32_t r[16];
+      tmem_ld16(taddr + g * 16, r);
+      tmem_ld_wait();
+      for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 128 + g * 16 + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
 int make_act_tmap(CUtensorMap* tm, const void* x, int B, int H, int W, int C, int box_w, int box_h,
                   int estride) {
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -467,6 +516,24 @@ extern "C" int cal_debug_shift_mma(const void* x_256x64, const void* w_64x64, in
   CAL_CHECK_CUDA(cudaFuncSetAttribute(shift_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   shift_mma_probe_kernel<<<1, 128, 256 * 128 + 64 * 128 + 1024, static_cast<cudaStream_t>(stream)>>>(
       tmX, tmW, shift, base_offset_mode, out_128x64);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int mode, float* out_128x128,
+                                void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(x_128x64 && y_64x128 && out_128x128, CAL_E_INVALID, "cal_debug_mn_mma: bad args");
+  CUtensorMap tmX, tmY;
+  const uint64_t dx[2] = {64, 128}, sx[1] = {128}, dy[2] = {128, 64}, sy[1] = {256};
+  const uint32_t bx[2] = {64, 128}, by[2] = {64, 64};
+  int rc = encode_tmap_f16(&tmX, x_128x64, 2, dx, sx, bx, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != CAL_OK) return rc;
+  rc = encode_tmap_f16(&tmY, y_64x128, 2, dy, sy, by, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != CAL_OK) return rc;
+  CAL_CHECK_CUDA(cudaFuncSetAttribute(mn_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  mn_mma_probe_kernel<<<1, 128, 128 * 128 + 2 * 8192 + 1024, static_cast<cudaStream_t>(stream)>>>(tmX, tmY, mode,
+                                                                                                  out_128x128);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
 }

@@ -19,6 +19,7 @@ tensor (hrnet.py:509) is never materialised.
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
@@ -292,6 +293,7 @@ class HRNetHeatmap:
         self._packed: Dict[str, _Packed] = {}
         self.device: Optional[torch.device] = None
         self.training = False
+        self.fused_head = os.environ.get("CAL_FUSED_HEAD", "1") != "0"
 
     # -- nn.Module-like surface used by the reference's callers
     def eval(self):
@@ -467,11 +469,18 @@ class HRNetHeatmap:
         else:
             full, full_key, low = ys[0], "head1.b0", list(enumerate(ys))[1:]
         proj = [self._conv(y, f"head1.b{i}", relu=False) for i, y in low]
-        u = torch.empty((B, h, w, cpad), dtype=torch.float16, device=self.device)
-        ops.fuse_combine(u, proj, self.head_b1, relu=False)
+        z = None
+        pf = self._packed[full_key]
+        if self.fused_head and full.shape[3] == 64:
+            # one kernel: W1_full * full + interpolation GEMMs over the projections + bias + ReLU
+            z = torch.empty((B, h, w, cpad), dtype=torch.float16, device=self.device)
+            z = ops.head_fused(full, pf.w, proj, self.head_b1, z, pf.rows)
+        if z is None:
+            u = torch.empty((B, h, w, cpad), dtype=torch.float16, device=self.device)
+            ops.fuse_combine(u, proj, self.head_b1, relu=False)
+            z = self._conv(full, full_key, relu=True, res=u)
+            del u
         del proj
-        z = self._conv(full, full_key, relu=True, res=u)
-        del u
         p2 = self._packed["head2"]
         heat = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=self.device)
         ops.conv2d(z, p2.w, p2.b, heat, ksize=1, stride=1, cout_rows=p2.rows, relu=False,

@@ -162,6 +162,39 @@ def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[t
     return y
 
 
+def head_fused(full: torch.Tensor, w_full: torch.Tensor, lows: Sequence[torch.Tensor], bias: torch.Tensor,
+               z: torch.Tensor, cout_rows: int) -> Optional[torch.Tensor]:
+    """z = relu(W1_full * full + sum_i up(low_i) + bias) (hrnet.py:489-511 up to the head's ReLU).
+    full (B,H,W,64) fp16 NHWC, w_full (rows,64), lows[i] (B,h_i,w_i,Cout_pad), z (B,H,W,Cout_pad).
+    Returns None when the kernel does not support the shape (caller takes the unfused path)."""
+    B, H, W, Cf = full.shape
+    a = _lib.HeadArgs()
+    a.full = _dev(full, torch.float16, "head full")
+    a.w_full = _dev(w_full, torch.float16, "head w_full")
+    if not 1 <= len(lows) <= 4:
+        raise _lib.CalError("head_fused: 1..4 low-resolution sources")
+    for i, t in enumerate(lows):
+        if t.shape[0] != B or t.shape[3] != z.shape[3]:
+            raise _lib.CalError("head_fused: source batch/channel mismatch")
+        a.low[i] = _dev(t, torch.float16, "head low")
+        a.low_h[i], a.low_w[i] = t.shape[1], t.shape[2]
+    a.n_low = len(lows)
+    a.bias = _dev(bias, torch.float32, "head bias")
+    a.z = _dev(z, torch.float16, "head z")
+    if tuple(z.shape[:3]) != (B, H, W) or w_full.shape[1] != Cf or w_full.shape[0] != cout_rows:
+        raise _lib.CalError("head_fused: shape mismatch")
+    a.B, a.H, a.W, a.Cf_pad, a.Cout_pad, a.Cout_rows = B, H, W, Cf, z.shape[3], cout_rows
+    name = "head_fused" if PROFILE is None else f"head_fused {Cf}->{z.shape[3]} @{H}x{W} n{len(lows)}"
+    with _Launch(name, full.device):
+        st = _lib.lib().cal_head_fused(C.byref(a), _stream())
+    if st == -2:                     # CAL_E_UNSUPPORTED
+        global LAUNCHES
+        LAUNCHES -= 1
+        return None
+    _lib.check(st, "cal_head_fused")
+    return z
+
+
 def tma_probe(x: torch.Tensor, box_w: int, box_h: int, estride: int, c0: int, x0: int, y0: int,
               n0: int) -> torch.Tensor:
     """Raw 16 KiB shared-memory image of one activation TMA box (tests only)."""

@@ -131,3 +131,47 @@ def test_stem_conv(B, H, W):
     ops.stem_conv(x, w.reshape(64, 27).contiguous(), b, y)
     got = packing.from_nhwc16(y, 64)
     assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("B,H,W,lows,cout", [
+    (2, 34, 48, [(17, 24), (9, 12), (5, 6), (3, 3)], 784),      # keypoint-style: x2, x4, x8, x16 below the head
+    (1, 270, 480, [(135, 240), (68, 120), (34, 60), (17, 30)], 784),
+    (2, 33, 60, [(17, 30), (9, 15), (5, 8)], 720),              # line-style: three lower branches, ragged tiles
+])
+def test_head_fused_vs_torch(B, H, W, lows, cout):
+    """cal_head_fused = relu(W_full * full + sum_i bilinear(p_i) + bias) against torch
+    (F.interpolate align_corners=True, the reference's op, hrnet.py:489-506)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    cpad = (cout + 63) // 64 * 64
+    full = torch.randn(B, 64, H, W, generator=g)
+    full[:, 48:] = 0                                             # padded channel lanes
+    wf = torch.randn(cout, 64, generator=g) / 8
+    ps = [torch.randn(B, cout, h, w, generator=g) for h, w in lows]
+    bias = torch.randn(cout, generator=g)
+    full16, wf16 = full.half(), wf.half()
+    ps16 = [t.half() for t in ps]
+    ref = F.conv2d(full16.float(), wf16.float()[:, :, None, None]) + bias[None, :, None, None]
+    for t in ps16:
+        ref = ref + F.interpolate(t.float(), size=(H, W), mode="bilinear", align_corners=True)
+    ref = ref.relu()
+
+    def nhwc(t, c):
+        out = torch.zeros(t.shape[0], t.shape[2], t.shape[3], c, dtype=torch.float16)
+        out[..., :t.shape[1]] = t.permute(0, 2, 3, 1)
+        return out.to(dev)
+    rows = (cout + 15) // 16 * 16
+    w_packed = torch.zeros(rows, 64, dtype=torch.float16)
+    w_packed[:cout] = wf16
+    bp = torch.zeros(cpad)
+    bp[:cout] = bias
+    z = torch.full((B, H, W, cpad), float("nan"), dtype=torch.float16, device=dev)
+    out = ops.head_fused(nhwc(full16, 64), w_packed.to(dev), [nhwc(t, cpad) for t in ps16], bp.to(dev), z, rows)
+    assert out is not None
+    got = out[..., :cout].permute(0, 3, 1, 2).float().cpu()
+    assert bool(torch.isfinite(out).all())
+    assert float(out[..., cout:].abs().max()) == 0.0             # pad lanes stay zero
+    err = (got - ref).abs()
+    # fp16 interpolation weights (2^-11 relative) + fp16 output rounding
+    assert float(err.max()) <= 2e-2 * max(1.0, float(ref.abs().max())) / 4
+    assert float(err.mean()) <= 2e-3

@@ -21,6 +21,8 @@
 //
 // L2 -> SM traffic per tile drops from 9 x 16 KB (+ all weights) to 25 KB (+ nothing when the
 // weights are resident): the old per-tap kernel ran these layers at the L2 throughput cap.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cal {
@@ -31,23 +33,31 @@ constexpr int H_EPI_THREADS = 256;
 constexpr int H_MAX_A_STAGES = 4;
 constexpr int H_MAX_B_STAGES = 8;
 constexpr int H_TMEM_COLS = 512;
-constexpr int H_ACC_STRIDE = 256;
+constexpr int H_MAX_ACC = 8;              // TMEM accumulator stages (512 columns / N_tile)
 constexpr int H_MAX_BIAS = 1024;
 constexpr int H_STAGE_BLOCK = 128 * 128;  // staging: 128 rows x 64 fp16 per channel block
 
 struct HaloParams {
   int B, H, W, Cout_pad;
   int TWp, TW, R;
+  int dual, RI;            // dual: a work item is two vertically adjacent tiles sharing every weight slice; RI = rows per item
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int N_tile, mma_n, nblk, ncc;
-  int relu;
+  int n_acc, acc_stride;   // accumulator ring in TMEM: n_acc stages of acc_stride columns
+  int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
   int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
   int w_resident, b_stages, b_slice_bytes;
   uint32_t b_tx_bytes;
   const float* bias;
   const __half* res;
+  long long* dbg;          // profiling experiments only: per-role clock64 stamps of CTA 0 (CAL_DEBUG_TIMELINE)
 };
+
+#define H_STAMP(slot, tile_i, k)                                                              \
+  do {                                                                                         \
+    if (p.dbg && blockIdx.x == 0 && (tile_i) < 64) p.dbg[((slot) * 64 + (tile_i)) * 8 + (k)] = clock64(); \
+  } while (0)
 
 struct HTile { int n0, b, y0, x0; };
 
@@ -60,10 +70,40 @@ __device__ __forceinline__ HTile h_decode_tile(const HaloParams& p, int t) {
   mt /= p.tiles_x;
   const int tyi = mt % p.tiles_y;
   c.b = mt / p.tiles_y;
-  c.y0 = tyi * p.R;
+  c.y0 = tyi * p.RI;
   c.x0 = txi * p.TW;
   return c;
 }
+
+// Tile coordinates advanced by a fixed stride without divisions: the stride's mixed-radix digits
+// (N tile, x tile, y tile, frame) are computed once, each step is an add with carries.
+struct HTileIter {
+  int nt, txi, tyi, b;          // current digits
+  int dn, dx, dy, db;           // digits of the stride
+  __device__ __forceinline__ void init(const HaloParams& p, int t, int stride) {
+    nt = t % p.n_tiles; int mt = t / p.n_tiles;
+    txi = mt % p.tiles_x; mt /= p.tiles_x;
+    tyi = mt % p.tiles_y; b = mt / p.tiles_y;
+    dn = stride % p.n_tiles; int ms = stride / p.n_tiles;
+    dx = ms % p.tiles_x; ms /= p.tiles_x;
+    dy = ms % p.tiles_y; db = ms / p.tiles_y;
+  }
+  __device__ __forceinline__ void advance(const HaloParams& p) {
+    nt += dn;
+    int c = 0;
+    if (nt >= p.n_tiles) { nt -= p.n_tiles; c = 1; }
+    txi += dx + c; c = 0;
+    if (txi >= p.tiles_x) { txi -= p.tiles_x; c = 1; }
+    tyi += dy + c; c = 0;
+    if (tyi >= p.tiles_y) { tyi -= p.tiles_y; c = 1; }
+    b += db + c;
+  }
+  __device__ __forceinline__ HTile get(const HaloParams& p) const {
+    HTile c;
+    c.n0 = nt * p.N_tile; c.b = b; c.y0 = tyi * p.RI; c.x0 = txi * p.TW;
+    return c;
+  }
+};
 
 __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
@@ -87,8 +127,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* emptyB = fullB + H_MAX_B_STAGES;
   uint64_t* wfull = emptyB + H_MAX_B_STAGES;
   uint64_t* tfull = wfull + 1;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + H_MAX_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + H_MAX_ACC);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,7 +140,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(wfull, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.dual ? 8 : 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, H_TMEM_COLS);
@@ -119,12 +159,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const HTile tc = h_decode_tile(p, t);
+      HTileIter ti;
+      ti.init(p, blockIdx.x, gridDim.x);
+      int pi = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ti.advance(p), ++pi) {
+        const HTile tc = ti.get(p);
         for (int cc = 0; cc < p.ncc; ++cc) {
+          H_STAMP(0, pi, 0);
           mbar_wait(&emptyA[sa], pha ^ 1);
-          mbar_expect_tx(&fullA[sa], p.a_tx_bytes);
-          tma_load_4d(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
+          H_STAMP(0, pi, 1);
+          if (p.ablate & 8) {
+            mbar_arrive(&fullA[sa]);
+          } else {
+            mbar_expect_tx(&fullA[sa], p.a_tx_bytes);
+            tma_load_4d(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
+          }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           if (!RESIDENT) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -154,13 +203,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
     const uint32_t w0 = (smem_u32(sW) & 0x3FFFF) >> 4, w_tap = static_cast<uint32_t>(p.ncc * p.b_slice_bytes) >> 4,
                    w_cc = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int mi = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++mi) {
+      if (issuer) H_STAMP(1, mi, 0);
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * H_ACC_STRIDE;
+      if (issuer) H_STAMP(1, mi, 1);
+      const uint32_t d_tmem = tmem_base + as * (p.dual ? 2 * p.acc_stride : p.acc_stride);
+      const uint32_t d_tmem1 = d_tmem + p.acc_stride;          // second tile of a dual item
+      const uint32_t a_tile1 = static_cast<uint32_t>(p.R * p.TWp * 128) >> 4;
       for (int cc = 0; cc < p.ncc; ++cc) {
         mbar_wait(&fullA[sa], pha);
         tc_fence_after();
+        if (issuer) H_STAMP(1, mi, 2);
         const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + sa * p.a_stage_bytes) & 0x3FFFF) >> 4);
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -172,13 +227,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             b0 = desc0 | static_cast<uint64_t>((smem_u32(sW + sb * p.b_slice_bytes) & 0x3FFFF) >> 4);
           }
-          if (issuer) {
+          if (issuer && !(p.ablate & 4)) {
             const uint64_t at = a0 + tap_off[tap];
             umma_f16(d_tmem, at, b0, idesc, (cc | tap) != 0);
             umma_f16(d_tmem, at + 2, b0 + 2, idesc, 1);
             umma_f16(d_tmem, at + 4, b0 + 4, idesc, 1);
             umma_f16(d_tmem, at + 6, b0 + 6, idesc, 1);
+            if (p.dual) {
+              const uint64_t at1 = at + a_tile1;
+              umma_f16(d_tmem1, at1, b0, idesc, (cc | tap) != 0);
+              umma_f16(d_tmem1, at1 + 2, b0 + 2, idesc, 1);
+              umma_f16(d_tmem1, at1 + 4, b0 + 4, idesc, 1);
+              umma_f16(d_tmem1, at1 + 6, b0 + 6, idesc, 1);
+            }
             if (!RESIDENT) umma_commit(&emptyB[sb]);
+          } else if (issuer && !RESIDENT) {
+            umma_commit(&emptyB[sb]);
           }
           __syncwarp();
           if (!RESIDENT) {
@@ -190,9 +254,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
       }
       if (issuer) umma_commit(&tfull[as]);
+      if (issuer) H_STAMP(1, mi, 3);
       __syncwarp();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == p.n_acc) { as = 0; aphase ^= 1; }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -207,50 +271,75 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
     uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
     const bool prefetch_res = (p.res != nullptr) && groups_total <= 2;
+    // residual rows are fetched one of this group's tiles ahead (the accumulator ring lets the
+    // MMAs run far ahead, so nothing else would hide the read latency)
+    uint4 rnext[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
+    // single mode: the groups alternate over the items; dual mode: group g takes tile g of every item
+    const int t_start = blockIdx.x + (p.dual ? 0 : grp * gridDim.x);
+    const int t_step = (p.dual ? 1 : 2) * gridDim.x;
+    const int as_step = p.dual ? 1 : 2;
+    const int yoff = p.dual ? grp * p.R : 0;
+    const uint32_t col_off = p.dual ? grp * p.acc_stride : 0;
+    const uint32_t item_cols = p.dual ? 2 * p.acc_stride : p.acc_stride;
+    HTileIter ti, tn;                       // this group's current item and the one after it
+    ti.init(p, t_start, t_step);
+    tn = ti;
+    auto residual_row = [&](int t, const HTileIter& itr) -> const __half* {
+      if (t >= p.total_tiles) return nullptr;
+      const HTile c = itr.get(p);
+      const int yy = c.y0 + yoff + r, xq = c.x0 + xx;
+      if (!((xx < p.TW) && (yy < p.H) && (xq < p.W))) return nullptr;
+      return p.res + ((static_cast<size_t>(c.b) * p.H + yy) * p.W + xq) * p.Cout_pad + c.n0;
+    };
+    if (prefetch_res) {
+      const __half* r0 = residual_row(t_start, tn);
+      if (r0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < groups_total * 4) rnext[q] = __ldg(reinterpret_cast<const uint4*>(r0) + q);
+      }
+    }
+    int as = p.dual ? 0 : grp;               // single mode: n_acc is even, this group sees stages grp, grp+2, ...
     uint32_t aphase = 0;
-    int it = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-      if ((it & 1) != grp) continue;
-      const HTile tc = h_decode_tile(p, t);
-      const int y = tc.y0 + r, x = tc.x0 + xx;
+    int ei = 0;
+    for (int t = t_start; t < p.total_tiles; t += t_step, ++ei) {
+      if (leader) H_STAMP(2 + grp, ei, 0);
+      const HTile tc = ti.get(p);
+      ti.advance(p);
+      tn.advance(p);
+      const int ty0 = tc.y0 + yoff;
+      const int y = ty0 + r, x = tc.x0 + xx;
       const bool valid = (xx < p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tc.b) * p.H + y) * p.W + x;
       const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
       uint4 rpre[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) rpre[q] = make_uint4(0, 0, 0, 0);
-      if (prefetch_res && rrow) {
+      for (int q = 0; q < 8; ++q) rpre[q] = rnext[q];
+      if (prefetch_res) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < groups_total * 4) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
+        for (int q = 0; q < 8; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
+        const __half* rn = residual_row(t + t_step, tn);
+        if (rn) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q < groups_total * 4) rnext[q] = __ldg(reinterpret_cast<const uint4*>(rn) + q);
+        }
       }
       // this group's previous TMA stores must have finished reading its staging buffer
+      if (leader) H_STAMP(2 + grp, ei, 1);
       if (leader) bulk_wait_read();
+      if (leader) H_STAMP(2 + grp, ei, 2);
       named_bar_sync(1 + grp, 128);
-      mbar_wait(&tfull[grp], aphase);
+      if (leader) H_STAMP(2 + grp, ei, 3);
+      mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + grp * H_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
-      for (int g = 0; g < groups_total; ++g) {
-        uint4 rq[4];
-        if (prefetch_res) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rq[q] = (g == 0) ? rpre[q] : rpre[4 + q];
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
-          if (rrow) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
-          }
-        }
-        uint32_t acc[32];
-        if (g * 32 < p.mma_n) {
-          tmem_ld32(taddr + g * 32, acc);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = 0u;
-        }
+      if (leader) H_STAMP(2 + grp, ei, 4);
+      const uint32_t taddr = tmem_base + as * item_cols + col_off + (static_cast<uint32_t>(quarter * 32) << 16);
+      // bias / residual / ReLU on one 32-column group and its 4 swizzled 16-byte staging writes
+      auto finish_group = [&](const uint32_t (&acc)[32], const uint4 (&rq)[4], int g) {
+        if (p.ablate & 2) return;
         const float* bb = s_bias + tc.n0 + g * 32;
         uint8_t* blk = sStage + (g >> 1) * H_STAGE_BLOCK + m * 128;
 #pragma unroll
@@ -271,20 +360,49 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int chunk = ((g & 1) * 4 + q) ^ (m & 7);       // SWIZZLE_128B: 16-byte chunk index
           *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
+      };
+      {
+        for (int g = 0; g < groups_total; ++g) {
+          uint4 rq[4];
+          if (prefetch_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rq[q] = (g == 0) ? rpre[q] : rpre[4 + q];
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
+            if (rrow) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+            }
+          }
+          uint32_t acc[32];
+          if (g * 32 < p.mma_n) {
+            tmem_ld32(taddr + g * 32, acc);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0u;
+          }
+          finish_group(acc, rq, g);
+        }
       }
+      if (leader) H_STAMP(2 + grp, ei, 5);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[grp]);           // accumulator drained
+      if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
       fence_proxy_async();                                // staging writes -> visible to the TMA unit
+      if (leader) H_STAMP(2 + grp, ei, 6);
       named_bar_sync(1 + grp, 128);
-      if (leader) {
+      if (leader && !(p.ablate & 1)) {
         for (int kb = 0; kb < p.nblk; ++kb)
           for (int rr = 0; rr < p.R; ++rr)
-            if (tc.y0 + rr < p.H)
-              tma_store_4d(&tmY, sStage + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, tc.y0 + rr, tc.b);
+            if (ty0 + rr < p.H)
+              tma_store_4d(&tmY, sStage + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, ty0 + rr, tc.b);
         bulk_commit();
       }
-      aphase ^= 1;
+      if (leader) H_STAMP(2 + grp, ei, 7);
+      as += as_step;
+      if (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1; }
     }
     if (leader) bulk_wait_all();
   }
@@ -312,7 +430,6 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     if (best < 0 || cost < best) { best = cost; p.TWp = twp; p.TW = tw; p.R = r; }
   }
   p.tiles_x = (a->Wout + p.TW - 1) / p.TW;
-  p.tiles_y = (a->Hout + p.R - 1) / p.R;
   int n_tiles = 1;
   while (a->Cout_pad % (64 * n_tiles) != 0 || a->Cout_pad / n_tiles > 256) ++n_tiles;
   p.n_tiles = n_tiles;
@@ -321,16 +438,34 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   int rows_left = a->Cout_rows;                       // weight rows available to the last N tile
   p.mma_n = p.N_tile < rows_left ? p.N_tile : rows_left;
   if (n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;   // ragged last N tile: generic kernel
-  p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
   p.ncc = a->Cin_pad / 64;
   p.relu = a->relu;
+  { const char* e = getenv("CAL_DEBUG_ABLATE"); p.ablate = e ? atoi(e) : 0; }
+  {
+    // CAL_DEBUG_TIMELINE=<device pointer, hex>: 4 roles x 64 tiles x 8 stamps of long long
+    const char* e = getenv("CAL_DEBUG_TIMELINE");
+    p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
   p.bias = a->bias;
   p.res = reinterpret_cast<const __half*>(a->res);
-  p.a_stage_bytes = (p.R + 2) * p.TWp * 128 + 1024;   // + pad rows read by the last taps of halo columns
-  p.a_tx_bytes = static_cast<uint32_t>((p.R + 2) * p.TWp * 128);
+  p.acc_stride = (p.N_tile + 31) & ~31;
+  // dual items (two tiles per weight slice: half the weight traffic, half the per-item handshakes)
+  // whenever two items of two accumulators each still fit the 512 TMEM columns
+  {
+    static const bool allow_dual = [] { const char* e = getenv("CAL_CONV_DUAL"); return !(e && e[0] == '0'); }();
+    p.dual = (allow_dual && 4 * p.acc_stride <= H_TMEM_COLS && a->Hout > p.R) ? 1 : 0;
+  }
+  p.RI = p.R * (1 + p.dual);
+  p.tiles_y = (a->Hout + p.RI - 1) / p.RI;
+  p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
+  p.a_stage_bytes = (p.RI + 2) * p.TWp * 128 + 1024;   // + pad rows read by the last taps of halo columns
+  p.a_tx_bytes = static_cast<uint32_t>((p.RI + 2) * p.TWp * 128);
   p.b_slice_bytes = ((p.mma_n * 128) + 1023) & ~1023;
   p.b_tx_bytes = static_cast<uint32_t>(p.mma_n * 128);
-  const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 5) * 8 + 16 + H_MAX_BIAS * 4;
+  p.n_acc = H_TMEM_COLS / (p.acc_stride * (1 + p.dual));
+  if (p.n_acc > H_MAX_ACC) p.n_acc = H_MAX_ACC;
+  if (!p.dual) p.n_acc &= ~1;                         // single mode: stage parity == epilogue group
+  const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + H_MAX_BIAS * 4;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
   // one staging buffer per epilogue group
   p.out_bufs = 2;
@@ -360,7 +495,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     const uint64_t dims[4] = {(uint64_t)a->Cin_pad, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
     const uint64_t strides[3] = {(uint64_t)a->Cin_pad * 2, (uint64_t)a->Win * a->Cin_pad * 2,
                                  (uint64_t)a->Hin * a->Win * a->Cin_pad * 2};
-    const uint32_t box[4] = {64, (uint32_t)p.TWp, (uint32_t)(p.R + 2), 1};
+    const uint32_t box[4] = {64, (uint32_t)p.TWp, (uint32_t)(p.RI + 2), 1};
     int rc = encode_tmap_f16(&tmA, a->x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
   }

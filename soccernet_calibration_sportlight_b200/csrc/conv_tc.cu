@@ -31,7 +31,7 @@ constexpr int A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 fp16
 constexpr int KC = 64;                     // K elements per pipeline stage
 constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
-constexpr int ACC_STRIDE = 256;            // TMEM column offset of accumulator stage 1
+constexpr int MAX_ACC = 8;                 // TMEM accumulator ring: up to 8 stages (512 columns / N_tile)
 constexpr int MAX_BIAS = 1024;
 
 struct ConvParams {
@@ -42,6 +42,7 @@ struct ConvParams {
   int kc_per_tap, taps, stride, pad, num_k;
   int relu, mode, n_classes;
   int stages, b_stage_bytes;
+  int n_acc, acc_stride;
   uint32_t tx_bytes;
   const float* bias;
   const __half* res;
@@ -81,8 +82,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* full = bars;
   uint64_t* empty = bars + MAX_STAGES;
   uint64_t* tfull = bars + 2 * MAX_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + MAX_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + MAX_ACC);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -91,7 +92,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int a = 0; a < MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -133,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
+      const uint32_t d_tmem = tmem_base + as * p.acc_stride;
       for (int k = 0; k < p.num_k; ++k) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -152,80 +153,101 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (issuer) umma_commit(&tfull[as]);        // accumulator complete -> epilogue
       __syncwarp();
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
+      if (++as == p.n_acc) { as = 0; aphase ^= 1; }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
+    // Two groups of four warps ping-pong over the tiles (group g owns accumulator stage g), so
+    // one tile's TMEM-load / residual-read / store chain overlaps the other group's.
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;             // which half of the column groups
-    const int groups_total = p.N_tile >> 4;
-    const int groups_mma = p.mma_n >> 4;
-    const int g_split = (groups_total + 1) >> 1;
-    const int g_begin = (p.mode == 0) ? (half ? g_split : 0) : 0;
-    const int g_end = (p.mode == 0) ? (half ? groups_total : g_split) : (half ? 0 : groups_total);
+    const int grp = (warp - 2) >> 2;
+    const int groups_total = (p.N_tile + 31) >> 5;   // 32-column groups
     const int m = quarter * 32 + lane;
     const int ty = m / p.TW, tx = m - ty * p.TW;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int as = it % p.n_acc;
+      const uint32_t aphase = static_cast<uint32_t>(it / p.n_acc) & 1u;
       const TileCoord tc = decode_tile(p, t);
       const int y = tc.y0 + ty, x = tc.x0 + tx;
       const bool valid = (m < p.TW * p.TH) && (y < p.Hout) && (x < p.Wout);
       const size_t pix = (static_cast<size_t>(tc.b) * p.Hout + y) * p.Wout + x;
+      const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
+      uint4 rpre[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) rpre[q] = make_uint4(0, 0, 0, 0);
+      const bool prefetch_res = groups_total <= 2;
+      if (prefetch_res && rrow) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q * 8 < p.N_tile) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
       if (p.mode == 0) {
         __half* yrow = reinterpret_cast<__half*>(p.y) + pix * p.Cout_pad + tc.n0;
-        const __half* rrow = p.res ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
-        for (int g = g_begin; g < g_end; ++g) {
-          uint4 rq0 = make_uint4(0, 0, 0, 0), rq1 = rq0;
-          if (rrow && valid) {
-            rq0 = __ldg(reinterpret_cast<const uint4*>(rrow + g * 16));
-            rq1 = __ldg(reinterpret_cast<const uint4*>(rrow + g * 16 + 8));
-          }
-          float v[16];
-          if (g < groups_mma) {
-            uint32_t r[16];
-            tmem_ld16(taddr + g * 16, r);
-            tmem_ld_wait();
+        for (int g = 0; g < groups_total; ++g) {
+          uint4 rq[4];
+          if (prefetch_res) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+            for (int q = 0; q < 4; ++q) rq[q] = (g == 0) ? rpre[q] : rpre[4 + q];
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+            for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
+            if (rrow) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (g * 32 + q * 8 < p.N_tile) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+            }
+          }
+          uint32_t acc[32];
+          if (g * 32 < p.mma_n) {
+            tmem_ld32(taddr + g * 32, acc);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0u;
           }
           if (valid) {
-            const float* bb = s_bias + tc.n0 + g * 16;
-            const uint32_t rr[8] = {rq0.x, rq0.y, rq0.z, rq0.w, rq1.x, rq1.y, rq1.z, rq1.w};
-            uint32_t o[8];
+            const float* bb = s_bias + tc.n0 + g * 32;
+            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
-              float a = v[2 * j] + bb[2 * j] + __low2float(rh);
-              float b = v[2 * j + 1] + bb[2 * j + 1] + __high2float(rh);
-              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-              o[j] = pack_half2(a, b);
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = q * 8 + 2 * j;
+                const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+                float a = (g * 32 + c < p.mma_n) ? __uint_as_float(acc[c]) : 0.0f;
+                float b = (g * 32 + c + 1 < p.mma_n) ? __uint_as_float(acc[c + 1]) : 0.0f;
+                a += bb[c] + __low2float(rh);
+                b += bb[c + 1] + __high2float(rh);
+                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                o[q * 4 + j] = pack_half2(a, b);
+              }
             }
-            *reinterpret_cast<uint4*>(yrow + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(yrow + g * 16 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+            // 32 channels = 64 bytes = two full sectors per pixel row
+            if (g * 32 + 16 <= p.N_tile) stg_v8(yrow + g * 32, o);
+            if (g * 32 + 32 <= p.N_tile) stg_v8(yrow + g * 32 + 16, o + 8);
           }
         }
-      } else if (half == 0) {
+      } else {
         // (Log)Softmax over the first n_classes columns of this pixel row, fp32 NCHW out
         float v[64];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (g < groups_mma) {
-            uint32_t r[16];
-            tmem_ld16(taddr + g * 16, r);
+        for (int g = 0; g < 2; ++g) {
+          if (g * 32 < p.mma_n) {
+            uint32_t r[32];
+            tmem_ld32(taddr + g * 32, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[g * 16 + j] = __uint_as_float(r[j]) + s_bias[g * 16 + j];
+            for (int j = 0; j < 32; ++j)
+              v[g * 32 + j] = (g * 32 + j < p.mma_n) ? __uint_as_float(r[j]) + s_bias[g * 32 + j] : 0.0f;
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[g * 16 + j] = 0.0f;
+            for (int j = 0; j < 32; ++j) v[g * 32 + j] = 0.0f;
           }
         }
         if (valid) {
@@ -251,8 +273,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
-      as ^= 1;
-      if (as == 0) aphase ^= 1;
     }
   }
 
@@ -451,7 +471,11 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
   p.bias = a->bias; p.res = reinterpret_cast<const __half*>(a->res); p.y = a->y;
   p.b_stage_bytes = ((p.mma_n * 128) + 1023) & ~1023;
   const int stage_bytes = A_STAGE_BYTES + p.b_stage_bytes;
-  const int tail_bytes = (2 * MAX_STAGES + 4) * 8 + 16 + MAX_BIAS * 4;
+  p.acc_stride = (p.N_tile + 31) & ~31;
+  if (p.mode != 0) p.acc_stride = 64;
+  p.n_acc = TMEM_COLS / p.acc_stride;
+  if (p.n_acc > MAX_ACC) p.n_acc = MAX_ACC;
+  const int tail_bytes = (2 * MAX_STAGES + 2 * MAX_ACC) * 8 + 16 + MAX_BIAS * 4;
   int stages = (200 * 1024 - tail_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   CAL_REQUIRE(stages >= 2, CAL_E_UNSUPPORTED, "cal_conv2d: tile does not fit shared memory");

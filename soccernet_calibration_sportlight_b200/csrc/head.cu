@@ -247,19 +247,16 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_fused_kernel(const __grid_
             tmem_ld_wait();
             if (valid) {
               const float* bb = s_bias + n0 + g * 32;
+              uint32_t o[16];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                if (g * 32 + q * 8 >= p.N_tile) break;
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int c = q * 8 + 2 * j;
-                  const float a = fmaxf(__uint_as_float(acc[c]) + bb[c], 0.0f);
-                  const float bq = fmaxf(__uint_as_float(acc[c + 1]) + bb[c + 1], 0.0f);
-                  o[j] = hd_pack_half2(a, bq);
-                }
-                *reinterpret_cast<uint4*>(zrow + n0 + g * 32 + q * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+              for (int j = 0; j < 16; ++j) {
+                const float a = fmaxf(__uint_as_float(acc[2 * j]) + bb[2 * j], 0.0f);
+                const float bq = fmaxf(__uint_as_float(acc[2 * j + 1]) + bb[2 * j + 1], 0.0f);
+                o[j] = hd_pack_half2(a, bq);
               }
+              // 32 channels = 64 bytes = two full 32-byte sectors per pixel row (N_tile is a multiple of 16)
+              if (g * 32 + 16 <= p.N_tile) stg_v8(zrow + n0 + g * 32, o);
+              if (g * 32 + 32 <= p.N_tile) stg_v8(zrow + n0 + g * 32 + 16, o + 8);
             }
           }
           tc_fence_before();

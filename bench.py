@@ -155,7 +155,7 @@ def run_reference(args, rank):
     from tests import inputs as I
     cores = os.cpu_count() or 1
     path = CpuPath(args.workload, cores)
-    frames = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, H_IMG, W_IMG)))
+    frames = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, *args.net_hw)))
     synth = synthetic_keypoints(args.steps + args.warmup, seed=5) if WORKLOADS[args.workload][2] else None
     for i in range(args.warmup):
         path(frames, None if synth is None else synth[i:i + 1])
@@ -198,7 +198,8 @@ def run_b200(args, rank, world, local_rank):
     pipe = CalibrationPipeline(dev, workload=args.workload, size=(H_IMG, W_IMG))
 
     g = torch.Generator().manual_seed(1234 + rank)
-    host = torch.randint(0, 256, (B, 3, H_IMG, W_IMG), generator=g, dtype=torch.uint8).float().div_(255.0).pin_memory()
+    nh, nw = args.net_hw
+    host = torch.randint(0, 256, (B, 3, nh, nw), generator=g, dtype=torch.uint8).float().div_(255.0).pin_memory()
     frames = host.to(dev)
     synth = None
     if solve:
@@ -279,19 +280,22 @@ def run_b200(args, rank, world, local_rank):
             for k, (t, n) in sorted(by_shape.items(), key=lambda kv: -kv[1][0]):
                 f.write(f"{k},{n},{t:.3f},{t / n * 1e3:.1f}\n")
     pk = peaks()
-    conv_ms, conv_n = per.get("conv_tc", [0.0, 0])
-    gflop_frame = sum(P.conv_gflop_per_frame(k, H_IMG, W_IMG) for k in nets)
-    stem_gflop = 2.0 * 3 * 64 * 9 * 270 * 480 / 1e9 * len(nets)      # conv1 runs on CUDA cores (stem_conv)
+    # every tcgen05 conv launch: generic + halo kernels ("conv_tc") and the fused head
+    conv_ms = per.get("conv_tc", [0.0, 0])[0] + per.get("head_fused", [0.0, 0])[0]
+    conv_n = per.get("conv_tc", [0.0, 0])[1] + per.get("head_fused", [0.0, 0])[1]
+    gflop_frame = sum(P.conv_gflop_per_frame(k, nh, nw) for k in nets)
+    stem_gflop = 2.0 * 3 * 64 * 9 * ((nh + 1) // 2) * ((nw + 1) // 2) / 1e9 * len(nets)   # conv1 runs on CUDA cores (stem_conv)
     conv_tflop = (gflop_frame - stem_gflop) * B / 1e3
     achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
-    roof = {"kernel": "conv_tc_kernel (tcgen05 implicit GEMM, all conv launches of one step)", "bound": "tensor",
+    roof = {"kernel": "tcgen05 implicit-GEMM convs (conv3x3_halo_kernel + conv_tc_kernel + head_fused_kernel, all "
+                      "launches of one step)", "bound": "tensor",
             "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tensor_sustained"], "peak_source": pk["source"] + " (sustained fp16/bf16 dense)",
             "launches_per_step": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
             "algorithmic_tflop_per_step": conv_tflop, "share_of_step": conv_ms / (ms / args.steps), "traffic": None}
     dec = {}
     if "kp_decode" in per:
-        bytes_alg = B * 57 * (H_IMG // 2) * (W_IMG // 2) * 4
+        bytes_alg = B * 57 * ((nh + 1) // 2) * ((nw + 1) // 2) * 4
         t = per["kp_decode"][0] / 1e3
         dec = {"kernel": "kp_decode_vec_kernel", "bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": pk["hbm"],
                "unit": "GB/s", "frac": bytes_alg / t / 1e9 / pk["hbm"], "ms": per["kp_decode"][0]}
@@ -306,7 +310,7 @@ def run_b200(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (tcgen05); f32 decode; f64 camera solve",
         "data": "synthetic",
         "config": {"workload": desc, "name": args.workload, "batch_per_gpu": B, "global_batch": world * B,
-                   "resolution": [W_IMG, H_IMG], "weights": "random-init HRNet-w48 (seeded)",
+                   "resolution": [nw, nh], "weights": "random-init HRNet-w48 (seeded)",
                    "l2": "inputs larger than L2 (398 MB of frames + GBs of activations per step)",
                    "parallelism": f"frame shards x{world}, one NCCL all-gather of the results" if world > 1 else "single GPU"},
         "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -324,7 +328,7 @@ def cpu_baseline(args):
     cores = os.cpu_count() or 1
     path = CpuPath(args.workload, cores)
     n = args.cpu_frames
-    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, H_IMG, W_IMG)))
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(1, 1, *args.net_hw)))
     solve = WORKLOADS[args.workload][2]
     synth = synthetic_keypoints(n + 1, seed=5) if solve else None
     path(x, None if synth is None else synth[:1])            # warm-up frame
@@ -344,10 +348,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("CAL_BENCH_WORKLOAD", "full"), choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
+    ap.add_argument("--height", type=int, default=H_IMG, help="network input height (BASELINE config 5 sweep: 540/720/1080)")
+    ap.add_argument("--width", type=int, default=W_IMG)
     ap.add_argument("--cpu-frames", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shapes-out", default="", help="write per-(kernel, shape) device times of one profiled step")
     args = ap.parse_args()
+    # the network runs at --height x --width; keypoints stay in 960x540 coordinates (the camera
+    # solve's hard-coded IMG_SIZE, prediction.py:24, 622-629), as the decode's `size` argument does
+    NET_H, NET_W = args.height, args.width
+    args.net_hw = (NET_H, NET_W)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -85,6 +85,7 @@ typedef struct CalConvArgs {
   int32_t mode;      /* 0 = fp16 NHWC; 1 = LogSoftmax over n_classes -> fp32 NCHW
                         (hrnet.py:329); 2 = Softmax (line/hrnet.py:101) */
   int32_t n_classes; /* modes 1/2: 58 / 23 */
+  int32_t Cin;       /* real input channels (<= Cin_pad; 0 = Cin_pad): K steps over pad lanes are skipped */
 } CalConvArgs;
 
 /* conv (+folded BN) (+residual) (+ReLU) as an implicit GEMM on tcgen05/TMEM with

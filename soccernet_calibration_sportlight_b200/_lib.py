@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin_pad", C.c_int32),
                 ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout_pad", C.c_int32),
                 ("Cout_rows", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
-                ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32)]
+                ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32), ("Cin", C.c_int32)]
 
 
 class CombineArgs(C.Structure):

@@ -40,9 +40,11 @@ constexpr int H_STAGE_BLOCK = 128 * 128;  // staging: 128 rows x 64 fp16 per cha
 struct HaloParams {
   int B, H, W, Cout_pad;
   int TWp, TW, R;
+  int cluster, part_rows, n_slowest;   // weight slices multicast over `cluster` CTAs, part_rows rows loaded by each
   int dual, RI;            // dual: a work item is two vertically adjacent tiles sharing every weight slice; RI = rows per item
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int N_tile, mma_n, nblk, ncc;
+  int ksteps_last;         // K = 16 steps of the last 64-channel chunk that hold real channels
   int n_acc, acc_stride;   // accumulator ring in TMEM: n_acc stages of acc_stride columns
   int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
   int a_stages, a_stage_bytes, out_bufs;
@@ -78,29 +80,30 @@ __device__ __forceinline__ HTile h_decode_tile(const HaloParams& p, int t) {
 // Tile coordinates advanced by a fixed stride without divisions: the stride's mixed-radix digits
 // (N tile, x tile, y tile, frame) are computed once, each step is an add with carries.
 struct HTileIter {
-  int nt, txi, tyi, b;          // current digits
-  int dn, dx, dy, db;           // digits of the stride
+  int d[4];                     // digits, fastest first: (nt, x, y, b), or (x, y, b, nt) when p.n_slowest
+  int s[4];                     // digits of the stride
+  int rad[3];                   // radices of the three lower digits
   __device__ __forceinline__ void init(const HaloParams& p, int t, int stride) {
-    nt = t % p.n_tiles; int mt = t / p.n_tiles;
-    txi = mt % p.tiles_x; mt /= p.tiles_x;
-    tyi = mt % p.tiles_y; b = mt / p.tiles_y;
-    dn = stride % p.n_tiles; int ms = stride / p.n_tiles;
-    dx = ms % p.tiles_x; ms /= p.tiles_x;
-    dy = ms % p.tiles_y; db = ms / p.tiles_y;
+    if (p.n_slowest) { rad[0] = p.tiles_x; rad[1] = p.tiles_y; rad[2] = p.B; }
+    else { rad[0] = p.n_tiles; rad[1] = p.tiles_x; rad[2] = p.tiles_y; }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { d[k] = t % rad[k]; t /= rad[k]; s[k] = stride % rad[k]; stride /= rad[k]; }
+    d[3] = t; s[3] = stride;
   }
-  __device__ __forceinline__ void advance(const HaloParams& p) {
-    nt += dn;
+  __device__ __forceinline__ void advance(const HaloParams&) {
     int c = 0;
-    if (nt >= p.n_tiles) { nt -= p.n_tiles; c = 1; }
-    txi += dx + c; c = 0;
-    if (txi >= p.tiles_x) { txi -= p.tiles_x; c = 1; }
-    tyi += dy + c; c = 0;
-    if (tyi >= p.tiles_y) { tyi -= p.tiles_y; c = 1; }
-    b += db + c;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d[k] += s[k] + c;
+      c = 0;
+      if (d[k] >= rad[k]) { d[k] -= rad[k]; c = 1; }
+    }
+    d[3] += s[3] + c;
   }
   __device__ __forceinline__ HTile get(const HaloParams& p) const {
     HTile c;
-    c.n0 = nt * p.N_tile; c.b = b; c.y0 = tyi * p.RI; c.x0 = txi * p.TW;
+    if (p.n_slowest) { c.x0 = d[0] * p.TW; c.y0 = d[1] * p.RI; c.b = d[2]; c.n0 = d[3] * p.N_tile; }
+    else { c.n0 = d[0] * p.N_tile; c.x0 = d[1] * p.TW; c.y0 = d[2] * p.RI; c.b = d[3]; }
     return c;
   }
 };
@@ -113,7 +116,8 @@ __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
 template <bool RESIDENT>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
+                    const __grid_constant__ CUtensorMap tmBp, const __grid_constant__ CUtensorMap tmY,
+                    const HaloParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -138,7 +142,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
     for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
+    for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], p.cluster); }
     mbar_init(wfull, 1);
     for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.dual ? 8 : 4); }
     fence_barrier_init();
@@ -147,8 +151,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   for (int i = threadIdx.x; i < p.Cout_pad; i += H_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
+  const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -177,9 +184,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           if (!RESIDENT) {
             for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&emptyB[sb], phb ^ 1);
+              mbar_wait(&emptyB[sb], phb ^ 1);           // freed by every CTA of the cluster
               mbar_expect_tx(&fullB[sb], p.b_tx_bytes);
-              tma_load_2d(sW + sb * p.b_slice_bytes, &tmB, &fullB[sb], (tap * p.ncc + cc) * 64, tc.n0);
+              if (p.cluster > 1)                         // this CTA's rows of the slice, to all peers
+                tma_load_2d_mcast(sW + sb * p.b_slice_bytes + crank * p.part_rows * 128, &tmBp, &fullB[sb],
+                                  (tap * p.ncc + cc) * 64, tc.n0 + static_cast<int>(crank) * p.part_rows, cmask);
+              else
+                tma_load_2d(sW + sb * p.b_slice_bytes, &tmB, &fullB[sb], (tap * p.ncc + cc) * 64, tc.n0);
               if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
             }
           }
@@ -217,6 +228,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         if (issuer) H_STAMP(1, mi, 2);
         const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + sa * p.a_stage_bytes) & 0x3FFFF) >> 4);
+        const int nk = (cc == p.ncc - 1) ? p.ksteps_last : 4;     // pad lanes of the last chunk are zero: skip them
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           uint64_t b0;
@@ -230,19 +242,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (issuer && !(p.ablate & 4)) {
             const uint64_t at = a0 + tap_off[tap];
             umma_f16(d_tmem, at, b0, idesc, (cc | tap) != 0);
-            umma_f16(d_tmem, at + 2, b0 + 2, idesc, 1);
-            umma_f16(d_tmem, at + 4, b0 + 4, idesc, 1);
-            umma_f16(d_tmem, at + 6, b0 + 6, idesc, 1);
+            if (nk > 1) umma_f16(d_tmem, at + 2, b0 + 2, idesc, 1);
+            if (nk > 2) umma_f16(d_tmem, at + 4, b0 + 4, idesc, 1);
+            if (nk > 3) umma_f16(d_tmem, at + 6, b0 + 6, idesc, 1);
             if (p.dual) {
               const uint64_t at1 = at + a_tile1;
               umma_f16(d_tmem1, at1, b0, idesc, (cc | tap) != 0);
-              umma_f16(d_tmem1, at1 + 2, b0 + 2, idesc, 1);
-              umma_f16(d_tmem1, at1 + 4, b0 + 4, idesc, 1);
-              umma_f16(d_tmem1, at1 + 6, b0 + 6, idesc, 1);
+              if (nk > 1) umma_f16(d_tmem1, at1 + 2, b0 + 2, idesc, 1);
+              if (nk > 2) umma_f16(d_tmem1, at1 + 4, b0 + 4, idesc, 1);
+              if (nk > 3) umma_f16(d_tmem1, at1 + 6, b0 + 6, idesc, 1);
             }
-            if (!RESIDENT) umma_commit(&emptyB[sb]);
+            if (!RESIDENT) { if (p.cluster > 1) umma_commit_mcast(&emptyB[sb], cmask); else umma_commit(&emptyB[sb]); }
           } else if (issuer && !RESIDENT) {
-            umma_commit(&emptyB[sb]);
+            if (p.cluster > 1) umma_commit_mcast(&emptyB[sb], cmask); else umma_commit(&emptyB[sb]);
           }
           __syncwarp();
           if (!RESIDENT) {
@@ -409,6 +421,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();      // no CTA leaves while a peer may still write into it
   if (warp == 1) tmem_dealloc(tmem_base, H_TMEM_COLS);
 }
 
@@ -439,6 +452,12 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   p.mma_n = p.N_tile < rows_left ? p.N_tile : rows_left;
   if (n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;   // ragged last N tile: generic kernel
   p.ncc = a->Cin_pad / 64;
+  {
+    const int cin = (a->Cin > 0 && a->Cin <= a->Cin_pad) ? a->Cin : a->Cin_pad;
+    p.ksteps_last = (cin - (p.ncc - 1) * 64 + 15) / 16;
+    if (p.ksteps_last < 1) p.ksteps_last = 1;
+    if (p.ksteps_last > 4) p.ksteps_last = 4;
+  }
   p.relu = a->relu;
   { const char* e = getenv("CAL_DEBUG_ABLATE"); p.ablate = e ? atoi(e) : 0; }
   {
@@ -486,11 +505,34 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   }
   if (p.a_stages > H_MAX_A_STAGES) p.a_stages = H_MAX_A_STAGES;
   if (p.a_stages < 2) return CAL_E_UNSUPPORTED;
+  // streamed weights: multicast every slice over a cluster of 4 (or 2) CTAs - each loads a
+  // quarter (half) of the rows - so the L2 -> SM weight traffic per tile drops by the same factor
+  p.cluster = 1; p.n_slowest = 0; p.part_rows = p.mma_n;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    CAL_CHECK_CUDA(cudaGetDevice(&dev));
+    CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  if (!p.w_resident) {
+    static const int max_cluster = [] { const char* e = getenv("CAL_CONV_CLUSTER"); return e ? atoi(e) : 4; }();
+    const int m_items = a->B * p.tiles_x * p.tiles_y;
+    for (int cl = 4; cl >= 2; cl >>= 1) {
+      if (cl > max_cluster) continue;
+      if (grid % cl || p.total_tiles % cl || (p.mma_n / cl) % 8 || p.mma_n % cl) continue;
+      if (n_tiles > 1 && m_items % cl) continue;
+      p.cluster = cl; p.part_rows = p.mma_n / cl; p.n_slowest = n_tiles > 1 ? 1 : 0;
+      break;
+    }
+  }
   const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
   const size_t smem = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
                       static_cast<size_t>(w_slots) * p.b_slice_bytes + static_cast<size_t>(p.out_bufs) * p.nblk * H_STAGE_BLOCK + tail;
 
-  CUtensorMap tmA, tmB, tmY;
+  CUtensorMap tmA, tmB, tmBp, tmY;
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin_pad, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
     const uint64_t strides[3] = {(uint64_t)a->Cin_pad * 2, (uint64_t)a->Win * a->Cin_pad * 2,
@@ -506,6 +548,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     const uint32_t box[2] = {64, (uint32_t)p.mma_n};
     int rc = encode_tmap_f16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
+    const uint32_t boxp[2] = {64, (uint32_t)p.part_rows};
+    rc = encode_tmap_f16(&tmBp, a->w, 2, dims, strides, boxp, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != CAL_OK) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)a->Cout_pad, (uint64_t)a->Wout, (uint64_t)a->Hout, (uint64_t)a->B};
@@ -515,20 +560,22 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     int rc = encode_tmap_f16(&tmY, a->y, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
   }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    CAL_CHECK_CUDA(cudaGetDevice(&dev));
-    CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(H_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (p.w_resident)
-    conv3x3_halo_kernel<true><<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
+    CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true>, tmA, tmB, tmBp, tmY, p));
   else
-    conv3x3_halo_kernel<false><<<grid, H_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmY, p);
-  CAL_CHECK_CUDA(cudaGetLastError());
+    CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false>, tmA, tmB, tmBp, tmY, p));
   return CAL_OK;
 }
 

@@ -40,6 +40,7 @@ struct ConvParams {
   int N_tile;        // output-channel span of one tile in the padded channel space
   int mma_n;         // N of the MMA instruction (<= N_tile, multiple of 16)
   int kc_per_tap, taps, stride, pad, num_k;
+  int ksteps_last;   // K = 16 steps of the last channel chunk that hold real channels
   int relu, mode, n_classes;
   int stages, b_stage_bytes;
   int n_acc, acc_stride;
@@ -135,20 +136,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * p.acc_stride;
+      int cc_k = 0;
       for (int k = 0; k < p.num_k; ++k) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + stage * A_STAGE_BYTES) & 0x3FFFF) >> 4);
         const uint64_t b0 = desc0 | static_cast<uint64_t>((smem_u32(sB + stage * p.b_stage_bytes) & 0x3FFFF) >> 4);
         if (issuer) {
-          // +32 bytes per K=16 step inside the 128-byte swizzle span
+          // +32 bytes per K=16 step inside the 128-byte swizzle span; steps over pad lanes skipped
+          const int nk = (cc_k == p.kc_per_tap - 1) ? p.ksteps_last : 4;
           umma_f16(d_tmem, a0, b0, idesc, k != 0);
-          umma_f16(d_tmem, a0 + 2, b0 + 2, idesc, 1);
-          umma_f16(d_tmem, a0 + 4, b0 + 4, idesc, 1);
-          umma_f16(d_tmem, a0 + 6, b0 + 6, idesc, 1);
+          if (nk > 1) umma_f16(d_tmem, a0 + 2, b0 + 2, idesc, 1);
+          if (nk > 2) umma_f16(d_tmem, a0 + 4, b0 + 4, idesc, 1);
+          if (nk > 3) umma_f16(d_tmem, a0 + 6, b0 + 6, idesc, 1);
           umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
         }
         __syncwarp();
+        if (++cc_k == p.kc_per_tap) cc_k = 0;
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (issuer) umma_commit(&tfull[as]);        // accumulator complete -> epilogue
@@ -464,6 +468,12 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
   p.mma_n = p.N_tile < a->Cout_rows ? p.N_tile : a->Cout_rows;
   p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
   p.kc_per_tap = a->Cin_pad / KC;
+  {
+    const int cin = (a->Cin > 0 && a->Cin <= a->Cin_pad) ? a->Cin : a->Cin_pad;
+    p.ksteps_last = (cin - (p.kc_per_tap - 1) * KC + 15) / 16;
+    if (p.ksteps_last < 1) p.ksteps_last = 1;
+    if (p.ksteps_last > 4) p.ksteps_last = 4;
+  }
   p.taps = a->ksize * a->ksize;
   p.stride = a->stride; p.pad = pad;
   p.num_k = p.taps * p.kc_per_tap;

@@ -265,7 +265,7 @@ def init_state_dict(cfg: Config, kind: str, seed: int = 0) -> "OrderedDict[str, 
 
 # ------------------------------------------------------------------------------- the engine
 class _Packed:
-    __slots__ = ("w", "b", "rows", "cin_pad", "cout_pad", "k", "s")
+    __slots__ = ("w", "b", "rows", "cin_pad", "cout_pad", "k", "s", "cin")
 
 
 class HRNetHeatmap:
@@ -345,6 +345,7 @@ class HRNetHeatmap:
         p = _Packed()
         p.w, p.b, p.rows = wp.to(self.device), bp.to(self.device), rows
         p.cin_pad, p.cout_pad, p.k, p.s = packing.pad_to(w.shape[1]), bp.numel(), k, s
+        p.cin = int(w.shape[1])
         self._packed[key] = p
 
     def _pack(self):
@@ -385,7 +386,7 @@ class HRNetHeatmap:
         pad = p.k // 2
         Ho, Wo = (H + 2 * pad - p.k) // p.s + 1, (W + 2 * pad - p.k) // p.s + 1
         y = torch.empty((B, Ho, Wo, p.cout_pad), dtype=torch.float16, device=x.device)
-        return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res)
+        return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res, cin=p.cin)
 
     def _blocks(self, x, blocks):
         for convs, ds in blocks:
@@ -484,5 +485,5 @@ class HRNetHeatmap:
         p2 = self._packed["head2"]
         heat = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=self.device)
         ops.conv2d(z, p2.w, p2.b, heat, ksize=1, stride=1, cout_rows=p2.rows, relu=False,
-                   mode=1 if self.kind == "keypoints" else 2, n_classes=self.num_classes)
+                   mode=1 if self.kind == "keypoints" else 2, n_classes=self.num_classes, cin=p2.cin)
         return heat

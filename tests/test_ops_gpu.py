@@ -70,6 +70,11 @@ CONV_CASES = [
     dict(B=5, H=68, W=120, ci=96, co=96, k=3, s=1, res=True),
     dict(B=1, H=1, W=1, ci=64, co=64, k=3, s=1),
     dict(B=1, H=3, W=130, ci=48, co=48, k=3, s=1, res=True),
+    # persistent grids of 148 CTAs in clusters of 4 with multicast weight slices
+    dict(B=16, H=68, W=120, ci=96, co=96, k=3, s=1, res=True),
+    dict(B=8, H=34, W=60, ci=192, co=192, k=3, s=1, res=True),
+    dict(B=16, H=17, W=30, ci=384, co=384, k=3, s=1, res=True),     # two N tiles: N-slowest tile order
+    dict(B=9, H=34, W=60, ci=192, co=192, k=3, s=1),                # 162 items: clusters of 2
 ]
 
 

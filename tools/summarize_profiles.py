@@ -69,7 +69,7 @@ def full(name):
 
 
 launches()
-for n in sys.argv[3:] or ["conv", "decode", "solve", "combine"]:
+for n in sys.argv[3:] or ["halo", "convtc", "head", "combine", "decode", "linedecode", "solve", "stem", "conv"]:
     full(n)
 for fn in (f"{tag}_bench_{wl}.json", f"{tag}_bench_{wl}_ref.json", f"{tag}_smi.txt", f"{tag}_pytest_gpu.log"):
     if os.path.exists(os.path.join(OUT, fn)):

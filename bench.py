@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="frames per GPU per step")
     ap.add_argument("--height", type=int, default=H_IMG, help="network input height (BASELINE config 5 sweep: 540/720/1080)")
     ap.add_argument("--width", type=int, default=W_IMG)
-    ap.add_argument("--cpu-frames", type=int, default=12)
+    ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shapes-out", default="", help="write per-(kernel, shape) device times of one profiled step")
     args = ap.parse_args()

@@ -518,7 +518,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (!p.w_resident) {
-    static const int max_cluster = [] { const char* e = getenv("CAL_CONV_CLUSTER"); return e ? atoi(e) : 4; }();
+    static const int max_cluster = [] { const char* e = getenv("CAL_CONV_CLUSTER"); return e ? atoi(e) : 1; }();   // measured slower than unicast at 4 (lock-step stage recycling): opt-in
     const int m_items = a->B * p.tiles_x * p.tiles_y;
     for (int cl = 4; cl >= 2; cl >>= 1) {
       if (cl > max_cluster) continue;

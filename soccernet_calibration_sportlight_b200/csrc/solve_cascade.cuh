@@ -169,14 +169,14 @@ CAL_HD_NOINLINE inline bool calibrate_views(const Team& T, Workspace& ws, const 
     const bool ok = ws.flag != 0;
     T.sync();
     if (!ok) continue;
-    lm_solve(T, ws, 20);
+    lm_solve(T, ws, 12);
     unmirror_planar_views(T, ws);
 #ifdef CAL_SOLVE_DEBUG
     if (T.tid == 0) printf("  stage1 cost=%g iters=%d t0=(%g %g %g)\n", ws.cost, ws.iters, ws.pose[0].t[0], ws.pose[0].t[1], ws.pose[0].t[2]);
 #endif
     if (T.tid == 0) ws.use_f = 1;          // joint refinement of f and all poses
     T.sync();
-    lm_solve(T, ws, 50);
+    lm_solve(T, ws, 30);
     unmirror_planar_views(T, ws);
 #ifdef CAL_SOLVE_DEBUG
     if (T.tid == 0) printf("  stage2 cost=%g iters=%d f=%g t0=(%g %g %g)\n", ws.cost, ws.iters, ws.f, ws.pose[0].t[0], ws.pose[0].t[1], ws.pose[0].t[2]);
@@ -246,7 +246,7 @@ CAL_HD inline void store_pose(const Team& T, Workspace& ws, CamState* cam) {
 }
 CAL_HD_NOINLINE inline void refine_camera(const Team& T, Workspace& ws, const CalSolveParams& P, const Points& pts, CamState* cam) {
   load_matched(T, ws, P, pts, *cam);
-  lm_solve(T, ws, 50);
+  lm_solve(T, ws, 30);
   store_pose(T, ws, cam);
 }
 

@@ -415,7 +415,7 @@ CAL_HD_NOINLINE inline void lm_solve(const Team& T, Workspace& ws, int max_iter)
     T.sync();
     // damped steps until the cost decreases
     bool accepted = false;
-    for (int trial = 0; trial < 16; ++trial) {
+    for (int trial = 0; trial < 10; ++trial) {
       CAL_COUNT(g_lm_trials);
       for (int e = T.tid; e < P * P + P; e += T.nt) {
         if (e < P * P) {

@@ -66,3 +66,36 @@ class CalibrationPipeline:
             kp = out["keypoints"] if keypoints_override is None else keypoints_override
             out["cameras"] = self.camera_creator.batch_records(kp, line_pts)
         return out
+
+    @torch.no_grad()
+    def run_stream(self, host_batches, keypoints_override: Optional[torch.Tensor] = None, result_key: Optional[str] = None,
+                   to_host: bool = True):
+        """Generator over an iterable of pinned HOST frame batches: the host->device copy of batch
+        i+1 runs on a side stream while batch i computes, and each result is read back to the host
+        (``result_key`` defaults to 'cameras' when the solve is on, else 'keypoints').  This is the
+        loop ``make_submit.py:59-73`` runs with the copies taken off the critical path."""
+        key = result_key or ("cameras" if self.camera_creator is not None else "keypoints")
+        copy_stream = torch.cuda.Stream(device=self.device)
+        compute = torch.cuda.current_stream(self.device)
+        it = iter(host_batches)
+
+        def stage(h):
+            with torch.cuda.stream(copy_stream):
+                d = h.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = stage(next(it))
+            except StopIteration:
+                nxt = None
+            compute.wait_event(ev)
+            out = self(cur, keypoints_override=keypoints_override)
+            cur.record_stream(compute)
+            yield out[key].to("cpu") if to_host else out[key]

@@ -7,6 +7,7 @@ dbg = torch.zeros(4 * 64 * 8, dtype=torch.int64, device="cuda")
 os.environ["CAL_DEBUG_TIMELINE"] = hex(dbg.data_ptr())
 from soccernet_calibration_sportlight_b200 import ops
 C, H, W, B = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), 64
+LO = int(os.environ.get("LO", "20"))
 use_res = len(sys.argv) > 4 and sys.argv[4] == "res"
 cp = (C + 63) // 64 * 64
 x = torch.randn(B, H, W, cp, device="cuda").half()
@@ -22,9 +23,9 @@ names = {0: ["wait_emptyA", "got_emptyA"], 1: ["start", "got_tempty", "got_fullA
          2: ["begin", "pre_bulkwait", "post_bulkwait", "post_bar1", "got_tfull", "epi_done", "fenced", "stores_issued"]}
 for role, nm in ((0, "producer"), (1, "mma"), (2, "epi0"), (3, "epi1")):
     print(nm, names[min(role, 2)])
-    for i in range(20, 28):
+    for i in range(LO, LO + 8):
         row = d[role, i]
         print("   tile", i, [int(v - t0) if v > 0 else None for v in row[:len(names[min(role, 2)])]])
 for role, nm in ((1, "mma"), (2, "epi0")):
-    per = (d[role, 40, 0] - d[role, 20, 0]) / 20
+    per = (d[role, LO + 7, 0] - d[role, LO, 0]) / 7
     print(nm, "cycles per own iteration:", per)

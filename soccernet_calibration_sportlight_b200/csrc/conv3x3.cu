@@ -63,20 +63,6 @@ struct HaloParams {
 
 struct HTile { int n0, b, y0, x0; };
 
-__device__ __forceinline__ HTile h_decode_tile(const HaloParams& p, int t) {
-  HTile c;
-  const int nt = t % p.n_tiles;
-  int mt = t / p.n_tiles;
-  c.n0 = nt * p.N_tile;
-  const int txi = mt % p.tiles_x;
-  mt /= p.tiles_x;
-  const int tyi = mt % p.tiles_y;
-  c.b = mt / p.tiles_y;
-  c.y0 = tyi * p.RI;
-  c.x0 = txi * p.TW;
-  return c;
-}
-
 // Tile coordinates advanced by a fixed stride without divisions: the stride's mixed-radix digits
 // (N tile, x tile, y tile, frame) are computed once, each step is an add with carries.
 struct HTileIter {

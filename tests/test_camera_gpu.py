@@ -178,3 +178,21 @@ def test_pipeline_full_workload_runs_and_is_frame_independent():
     assert out["cameras"].shape == (3, 16)
     assert torch.equal(out["keypoints"][0], out["keypoints"][2])
     assert torch.equal(out["cameras"][0], out["cameras"][2])
+
+
+def test_run_stream_overlapped_copies_match_direct_calls():
+    """CalibrationPipeline.run_stream (host->device copy of batch i+1 on a side stream) gives the
+    same records as calling the pipeline on device-resident batches."""
+    from soccernet_calibration_sportlight_b200.pipeline import CalibrationPipeline
+    pipe = CalibrationPipeline(DEV, workload="keypoints", size=(96, 160))
+    kp = torch.from_numpy(CI.clean_predictions(2, seed=6)).to(DEV)
+    batches = [torch.from_numpy(I.frames_to_tensor(I.frames_u8(s, 2, 96, 160))).pin_memory() for s in (1, 2, 3)]
+    direct = [pipe(b.to(DEV), keypoints_override=kp) for b in batches]
+    streamed = list(pipe.run_stream(batches, keypoints_override=kp))
+    assert len(streamed) == 3
+    for d, s in zip(direct, streamed):
+        assert s.device.type == "cpu" and torch.equal(d["cameras"].cpu(), s)
+    kps = list(pipe.run_stream(batches, result_key="keypoints"))
+    for d, s in zip(direct, kps):
+        assert torch.equal(d["keypoints"].cpu(), s)
+    assert list(pipe.run_stream([])) == []

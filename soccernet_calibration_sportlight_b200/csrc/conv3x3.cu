@@ -201,17 +201,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t w0 = (smem_u32(sW) & 0x3FFFF) >> 4, w_tap = static_cast<uint32_t>(p.ncc * p.b_slice_bytes) >> 4,
                    w_cc = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
     int mi = 0;
+    bool pre = false;        // this item's tempty / first fullA were already waited for (see below)
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++mi) {
       if (issuer) H_STAMP(1, mi, 0);
-      mbar_wait(&tempty[as], aphase ^ 1);
-      tc_fence_after();
+      const bool has_next = t + static_cast<int>(gridDim.x) < p.total_tiles;
+      bool pre_next = false;
+      if (!pre) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+      }
       if (issuer) H_STAMP(1, mi, 1);
       const uint32_t d_tmem = tmem_base + as * (p.dual ? 2 * p.acc_stride : p.acc_stride);
       const uint32_t d_tmem1 = d_tmem + p.acc_stride;          // second tile of a dual item
       const uint32_t a_tile1 = static_cast<uint32_t>(p.R * p.TWp * 128) >> 4;
       for (int cc = 0; cc < p.ncc; ++cc) {
-        mbar_wait(&fullA[sa], pha);
-        tc_fence_after();
+        if (!(pre && cc == 0)) {
+          mbar_wait(&fullA[sa], pha);
+          tc_fence_after();
+        }
         if (issuer) H_STAMP(1, mi, 2);
         const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + sa * p.a_stage_bytes) & 0x3FFFF) >> 4);
         const int nk = (cc == p.ncc - 1) ? p.ksteps_last : 4;     // pad lanes of the last chunk are zero: skip them
@@ -246,6 +253,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (!RESIDENT) {
             if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
           }
+          if (RESIDENT && tap == 5 && cc == p.ncc - 1 && has_next) {
+            // The MMA queue still holds this item's last taps: take the next item's barrier
+            // waits (accumulator stage free, first operand tile landed) off the tensor pipe's
+            // critical path.
+            const int as_n = (as + 1 == p.n_acc) ? 0 : as + 1;
+            const uint32_t aph_n = (as_n == 0) ? (aphase ^ 1) : aphase;
+            mbar_wait(&tempty[as_n], aph_n ^ 1);
+            const int sa_n = (sa + 1 == p.a_stages) ? 0 : sa + 1;
+            const uint32_t pha_n = (sa_n == 0) ? (pha ^ 1) : pha;
+            mbar_wait(&fullA[sa_n], pha_n);
+            tc_fence_after();
+            pre_next = true;
+          }
         }
         if (issuer) umma_commit(&emptyA[sa]);
         __syncwarp();
@@ -255,6 +275,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (issuer) H_STAMP(1, mi, 3);
       __syncwarp();
       if (++as == p.n_acc) { as = 0; aphase ^= 1; }
+      pre = pre_next;
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -266,6 +287,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int groups_total = p.N_tile >> 5;                 // 32-column groups
     const int m = quarter * 32 + lane;
     const int r = m / p.TWp, xx = m - r * p.TWp;
+    const int ms = r * p.TW + xx;                            // row of this pixel in the dense R x TW staging tile
     const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
     uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
     const bool prefetch_res = (p.res != nullptr) && groups_total <= 2;
@@ -337,9 +359,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t taddr = tmem_base + as * item_cols + col_off + (static_cast<uint32_t>(quarter * 32) << 16);
       // bias / residual / ReLU on one 32-column group and its 4 swizzled 16-byte staging writes
       auto finish_group = [&](const uint32_t (&acc)[32], const uint4 (&rq)[4], int g) {
-        if (p.ablate & 2) return;
+        if ((p.ablate & 2) || xx >= p.TW) return;            // halo columns are not staged
         const float* bb = s_bias + tc.n0 + g * 32;
-        uint8_t* blk = sStage + (g >> 1) * H_STAGE_BLOCK + m * 128;
+        uint8_t* blk = sStage + (g >> 1) * H_STAGE_BLOCK + ms * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
@@ -355,7 +377,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
             o[j] = h_pack_half2(a, b);
           }
-          const int chunk = ((g & 1) * 4 + q) ^ (m & 7);       // SWIZZLE_128B: 16-byte chunk index
+          const int chunk = ((g & 1) * 4 + q) ^ (ms & 7);      // SWIZZLE_128B: 16-byte chunk index
           *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       };
@@ -392,10 +414,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (leader) H_STAMP(2 + grp, ei, 6);
       named_bar_sync(1 + grp, 128);
       if (leader && !(p.ablate & 1)) {
-        for (int kb = 0; kb < p.nblk; ++kb)
-          for (int rr = 0; rr < p.R; ++rr)
-            if (ty0 + rr < p.H)
-              tma_store_4d(&tmY, sStage + kb * H_STAGE_BLOCK + rr * p.TWp * 128, tc.n0 + kb * 64, tc.x0, ty0 + rr, tc.b);
+        // one store per 64-channel block: the R x TW box is dense in the staging tile; rows below
+        // the image and columns right of it are clipped by the TMA unit
+        if (ty0 < p.H)
+          for (int kb = 0; kb < p.nblk; ++kb)
+            tma_store_4d(&tmY, sStage + kb * H_STAGE_BLOCK, tc.n0 + kb * 64, tc.x0, ty0, tc.b);
         bulk_commit();
       }
       if (leader) H_STAMP(2 + grp, ei, 7);
@@ -542,7 +565,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     const uint64_t dims[4] = {(uint64_t)a->Cout_pad, (uint64_t)a->Wout, (uint64_t)a->Hout, (uint64_t)a->B};
     const uint64_t strides[3] = {(uint64_t)a->Cout_pad * 2, (uint64_t)a->Wout * a->Cout_pad * 2,
                                  (uint64_t)a->Hout * a->Wout * a->Cout_pad * 2};
-    const uint32_t box[4] = {64, (uint32_t)p.TW, 1, 1};
+    const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.R, 1};
     int rc = encode_tmap_f16(&tmY, a->y, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
   }

@@ -49,7 +49,8 @@ struct Team {
   int tid, nt;
   CAL_HD void sync() const {
 #if defined(__CUDA_ARCH__)
-    __syncthreads();
+    if (nt <= 32) __syncwarp();      // a one-warp team: barrier latency is what the solver is made of
+    else __syncthreads();
 #endif
   }
 };

@@ -128,8 +128,15 @@ typedef struct CalHeadArgs {
   int32_t low_h[CAL_MAX_LOW], low_w[CAL_MAX_LOW];
   int32_t n_low;
   const float* bias;     /* fp32 (Cout_pad): conv bias with BN folded */
-  void* z;               /* fp16 NHWC (B, H, W, Cout_pad) */
+  void* z;               /* fp16 NHWC (B, H, W, Cout_pad); unused (may be NULL) when w2 is given */
   int32_t B, H, W, Cf_pad, Cout_pad, Cout_rows;
+  /* optional chained tail: the final 1x1 conv + (Log)Softmax (hrnet.py:325-329, line/hrnet.py:97-101)
+     applied to the ReLU'd tile while it is still on chip, z never reaches HBM */
+  const void* w2;        /* fp16 (64, Cout_pad) K-major, rows >= n_classes zero; NULL = write z */
+  const float* bias2;    /* fp32 (64) */
+  float* heat;           /* fp32 NCHW (B, n_classes, H, W) */
+  int32_t n_classes;     /* <= 64 */
+  int32_t mode;          /* 1 = LogSoftmax, 2 = Softmax */
 } CalHeadArgs;
 
 /* z = ReLU( W1_full * full + sum_i bilinear_up(p_i) + bias ): the upsample + concat + first 1x1 conv

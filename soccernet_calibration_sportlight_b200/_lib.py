@@ -46,7 +46,9 @@ class HeadArgs(C.Structure):
                 ("low_h", C.c_int32 * 4), ("low_w", C.c_int32 * 4), ("n_low", C.c_int32),
                 ("bias", C.c_void_p), ("z", C.c_void_p),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cf_pad", C.c_int32),
-                ("Cout_pad", C.c_int32), ("Cout_rows", C.c_int32)]
+                ("Cout_pad", C.c_int32), ("Cout_rows", C.c_int32),
+                ("w2", C.c_void_p), ("bias2", C.c_void_p), ("heat", C.c_void_p),
+                ("n_classes", C.c_int32), ("mode", C.c_int32)]
 
 
 class SolveParams(C.Structure):

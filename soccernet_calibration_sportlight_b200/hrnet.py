@@ -294,6 +294,7 @@ class HRNetHeatmap:
         self.device: Optional[torch.device] = None
         self.training = False
         self.fused_head = os.environ.get("CAL_FUSED_HEAD", "1") != "0"
+        self.chained_head = os.environ.get("CAL_HEAD_CHAIN", "1") != "0"
 
     # -- nn.Module-like surface used by the reference's callers
     def eval(self):
@@ -378,6 +379,11 @@ class HRNetHeatmap:
         if w2.shape[-1] != 1:
             raise NotImplementedError("final_conv_kernel must be 1 (every shipped config)")
         self._put("head2", w2, b2, 1, 1, cout_pad=64)
+        # the chained head kernel wants the final conv as a full 64-row K-major tile
+        p2 = self._packed["head2"]
+        w64 = torch.zeros((64, p2.w.shape[1]), dtype=torch.float16, device=self.device)
+        w64[:p2.rows] = p2.w
+        self.head2_w64 = w64
 
     # -- launch helpers
     def _conv(self, x, key, relu, res=None):
@@ -472,6 +478,15 @@ class HRNetHeatmap:
         proj = [self._conv(y, f"head1.b{i}", relu=False) for i, y in low]
         z = None
         pf = self._packed[full_key]
+        p2 = self._packed["head2"]
+        if self.fused_head and self.chained_head and full.shape[3] == 64:
+            # the whole head in one kernel: first conv + interpolation GEMMs + ReLU, then the final
+            # 1x1 conv and (Log)Softmax on the tile while it is still on chip
+            heat = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=self.device)
+            out = ops.head_fused(full, pf.w, proj, self.head_b1, None, pf.rows, w2=self.head2_w64, bias2=p2.b, heat=heat,
+                                 mode=1 if self.kind == "keypoints" else 2)
+            if out is not None:
+                return out
         if self.fused_head and full.shape[3] == 64:
             # one kernel: W1_full * full + interpolation GEMMs over the projections + bias + ReLU
             z = torch.empty((B, h, w, cpad), dtype=torch.float16, device=self.device)
@@ -482,7 +497,6 @@ class HRNetHeatmap:
             z = self._conv(full, full_key, relu=True, res=u)
             del u
         del proj
-        p2 = self._packed["head2"]
         heat = torch.empty((B, self.num_classes, h, w), dtype=torch.float32, device=self.device)
         ops.conv2d(z, p2.w, p2.b, heat, ksize=1, stride=1, cout_rows=p2.rows, relu=False,
                    mode=1 if self.kind == "keypoints" else 2, n_classes=self.num_classes, cin=p2.cin)

@@ -164,28 +164,45 @@ def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[t
 
 
 def head_fused(full: torch.Tensor, w_full: torch.Tensor, lows: Sequence[torch.Tensor], bias: torch.Tensor,
-               z: torch.Tensor, cout_rows: int) -> Optional[torch.Tensor]:
+               z: Optional[torch.Tensor], cout_rows: int, *, w2: Optional[torch.Tensor] = None,
+               bias2: Optional[torch.Tensor] = None, heat: Optional[torch.Tensor] = None,
+               mode: int = 0) -> Optional[torch.Tensor]:
     """z = relu(W1_full * full + sum_i up(low_i) + bias) (hrnet.py:489-511 up to the head's ReLU).
     full (B,H,W,64) fp16 NHWC, w_full (rows,64), lows[i] (B,h_i,w_i,Cout_pad), z (B,H,W,Cout_pad).
+    With ``w2`` (64, Cout_pad), ``bias2`` (64) and ``heat`` (B, n_classes, H, W) fp32 the final 1x1
+    conv + LogSoftmax (mode 1) / Softmax (mode 2) is chained on chip (hrnet.py:325-329) and ``heat``
+    is returned instead of z.
     Returns None when the kernel does not support the shape (caller takes the unfused path)."""
     B, H, W, Cf = full.shape
+    chain = w2 is not None
+    cout_pad = w2.shape[1] if chain else z.shape[3]
     a = _lib.HeadArgs()
     a.full = _dev(full, torch.float16, "head full")
     a.w_full = _dev(w_full, torch.float16, "head w_full")
     if not 1 <= len(lows) <= 4:
         raise _lib.CalError("head_fused: 1..4 low-resolution sources")
     for i, t in enumerate(lows):
-        if t.shape[0] != B or t.shape[3] != z.shape[3]:
+        if t.shape[0] != B or t.shape[3] != cout_pad:
             raise _lib.CalError("head_fused: source batch/channel mismatch")
         a.low[i] = _dev(t, torch.float16, "head low")
         a.low_h[i], a.low_w[i] = t.shape[1], t.shape[2]
     a.n_low = len(lows)
     a.bias = _dev(bias, torch.float32, "head bias")
-    a.z = _dev(z, torch.float16, "head z")
-    if tuple(z.shape[:3]) != (B, H, W) or w_full.shape[1] != Cf or w_full.shape[0] != cout_rows:
+    if chain:
+        if tuple(w2.shape) != (64, cout_pad) or bias2.numel() != 64 or tuple(heat.shape[0:1] + heat.shape[2:]) != (B, H, W):
+            raise _lib.CalError("head_fused: chained tail shape mismatch")
+        a.w2 = _dev(w2, torch.float16, "head w2")
+        a.bias2 = _dev(bias2, torch.float32, "head bias2")
+        a.heat = _dev(heat, torch.float32, "head heat")
+        a.n_classes, a.mode = heat.shape[1], mode
+    else:
+        a.z = _dev(z, torch.float16, "head z")
+        if tuple(z.shape[:3]) != (B, H, W):
+            raise _lib.CalError("head_fused: shape mismatch")
+    if w_full.shape[1] != Cf or w_full.shape[0] != cout_rows:
         raise _lib.CalError("head_fused: shape mismatch")
-    a.B, a.H, a.W, a.Cf_pad, a.Cout_pad, a.Cout_rows = B, H, W, Cf, z.shape[3], cout_rows
-    name = "head_fused" if PROFILE is None else f"head_fused {Cf}->{z.shape[3]} @{H}x{W} n{len(lows)}"
+    a.B, a.H, a.W, a.Cf_pad, a.Cout_pad, a.Cout_rows = B, H, W, Cf, cout_pad, cout_rows
+    name = "head_fused" if PROFILE is None else f"head_fused{'+tail' if chain else ''} {Cf}->{cout_pad} @{H}x{W} n{len(lows)}"
     with _Launch(name, full.device):
         st = _lib.lib().cal_head_fused(C.byref(a), _stream())
     if st == -2:                     # CAL_E_UNSUPPORTED
@@ -193,7 +210,7 @@ def head_fused(full: torch.Tensor, w_full: torch.Tensor, lows: Sequence[torch.Te
         LAUNCHES -= 1
         return None
     _lib.check(st, "cal_head_fused")
-    return z
+    return heat if chain else z
 
 
 def tma_probe(x: torch.Tensor, box_w: int, box_h: int, estride: int, c0: int, x0: int, y0: int,

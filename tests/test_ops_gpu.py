@@ -180,3 +180,21 @@ def test_head_fused_vs_torch(B, H, W, lows, cout):
     # fp16 interpolation weights (2^-11 relative) + fp16 output rounding
     assert float(err.max()) <= 2e-2 * max(1.0, float(ref.abs().max())) / 4
     assert float(err.mean()) <= 2e-3
+
+    # chained tail: final 1x1 conv + (Log)Softmax on chip (hrnet.py:325-329 / line/hrnet.py:97-101)
+    ncls, mode = (58, 1) if cout == 784 else (23, 2)
+    w2 = (torch.randn(ncls, cout, generator=g) / 16).half()
+    b2 = torch.randn(ncls, generator=g)
+    zq = got.half().float()                                        # what the kernel feeds the second GEMM
+    logits = F.conv2d(zq, w2.float()[:, :, None, None]) + b2[None, :, None, None]
+    ref2 = torch.log_softmax(logits, 1) if mode == 1 else torch.softmax(logits, 1)
+    w2p = torch.zeros(64, cpad, dtype=torch.float16)
+    w2p[:ncls, :cout] = w2
+    b2p = torch.zeros(64)
+    b2p[:ncls] = b2
+    heat = torch.full((B, ncls, H, W), float("nan"), device=dev)
+    out2 = ops.head_fused(nhwc(full16, 64), w_packed.to(dev), [nhwc(t, cpad) for t in ps16], bp.to(dev), None, rows,
+                          w2=w2p.to(dev), bias2=b2p.to(dev), heat=heat, mode=mode)
+    assert out2 is not None and bool(torch.isfinite(out2).all())
+    e2 = (out2.cpu() - ref2).abs()
+    assert float(e2.max()) <= (0.05 if mode == 1 else 5e-3), float(e2.max())

@@ -9,6 +9,7 @@ round-trip.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import torch
@@ -28,6 +29,8 @@ class CalibrationPipeline:
         if workload not in ("kp_decode", "keypoints", "full"):
             raise ValueError(workload)
         self.device = torch.device(device)
+        self.two_streams = os.environ.get("CAL_TWO_STREAMS", "1") != "0"
+        self._side = None
         self.workload = workload
         self.size = (int(size[0]), int(size[1]))
         self.kp_model = metamodel.HRNetMetaModel({"nn_module": {"num_refinement_stages": 0},
@@ -57,11 +60,27 @@ class CalibrationPipeline:
         ``keypoints_override`` (B,57,3) feeds the camera solve instead of the network's own
         keypoints (benchmarks with random-init weights, whose confidences never pass a threshold)."""
         x = frames.to(self.device, non_blocking=True)
-        out = {"keypoints": self.kp_model.predict(x)}
         line_pts = None
-        if self.line_model is not None:
-            out["lines"] = self.line_model.predict(x)
+        if self.line_model is not None and self.two_streams:
+            # the two networks are independent: on two streams the ramp-up / tail of every
+            # (persistent, one CTA per SM) kernel of one network is filled by the other's
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                lines = self.line_model.predict(x)
+            out = {"keypoints": self.kp_model.predict(x)}
+            main.wait_stream(self._side)
+            x.record_stream(self._side)
+            lines.record_stream(main)
+            out["lines"] = lines
             line_pts = self.camera_creator.line_points_device(out["lines"])
+        else:
+            out = {"keypoints": self.kp_model.predict(x)}
+            if self.line_model is not None:
+                out["lines"] = self.line_model.predict(x)
+                line_pts = self.camera_creator.line_points_device(out["lines"])
         if self.camera_creator is not None:
             kp = out["keypoints"] if keypoints_override is None else keypoints_override
             out["cameras"] = self.camera_creator.batch_records(kp, line_pts)

@@ -86,6 +86,9 @@ typedef struct CalConvArgs {
                         (hrnet.py:329); 2 = Softmax (line/hrnet.py:101) */
   int32_t n_classes; /* modes 1/2: 58 / 23 */
   int32_t Cin;       /* real input channels (<= Cin_pad; 0 = Cin_pad): K steps over pad lanes are skipped */
+  int32_t w_slices;  /* 0: w is (Cout_rows, taps*Cin_pad) K-major;
+                        1: w is slice-major (taps*Cin_pad/64, Cout_rows, 64): every (tap, 64-channel chunk)
+                           slice is one contiguous block - what a streamed weight ring wants (3x3 stride-1 only) */
 } CalConvArgs;
 
 /* conv (+folded BN) (+residual) (+ReLU) as an implicit GEMM on tcgen05/TMEM with
@@ -221,6 +224,15 @@ int cal_debug_shift_mma(const void* x_256x64, const void* w_64x64, int shift,
  * fused head's interpolation GEMM: D(128x128 fp32) = X(128x64) * Y(64x128), Y row-major. */
 int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int mode, float* out_128x128,
                      void* stream);
+
+/* Experiment: cycles for `iters` back-to-back tcgen05.mma (M = 128, K = 16) as a function of N, of the
+ * row shift of the A operand's start address and of `flags`: bit 0 = MN-major B operand, bits 8-15 =
+ * a tcgen05.commit after every that many groups of 4 MMAs (a power of two; 0: only at the end), bit 1 =
+ * also an mbarrier wait after each such commit, bit 3 = also a tcgen05.fence::after_thread_sync, bit 4 / bit 5 =
+ * that wait is an mbarrier.test_wait / a plain shared-memory flag poll instead of mbarrier.try_wait, bit 6 = the wait goes before the commit, bit 2 = issue no MMAs (commits only),
+ * bits 16-23 = CTAs launched (0: one); out_cycles has one
+ * entry per CTA. */
+int cal_debug_mma_rate(int N, int shift_rows, int iters, int flags, long long* out_cycles, void* stream);
 
 #ifdef __cplusplus
 }

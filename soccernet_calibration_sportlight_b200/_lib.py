@@ -14,7 +14,7 @@ EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points",
-    "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma",
+    "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",
 ]
 
 
@@ -28,7 +28,7 @@ class ConvArgs(C.Structure):
                 ("B", C.c_int32), ("Hin", C.c_int32), ("Win", C.c_int32), ("Cin_pad", C.c_int32),
                 ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout_pad", C.c_int32),
                 ("Cout_rows", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
-                ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32), ("Cin", C.c_int32)]
+                ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32), ("Cin", C.c_int32), ("w_slices", C.c_int32)]
 
 
 class CombineArgs(C.Structure):
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
     L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     L.cal_debug_shift_mma.argtypes = [vp, vp, i32, i32, vp, vp]
     L.cal_debug_mn_mma.argtypes = [vp, vp, i32, vp, vp]
+    L.cal_debug_mma_rate.argtypes = [i32, i32, i32, i32, vp, vp]
     L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
     L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]

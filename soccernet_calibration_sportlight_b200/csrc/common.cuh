@@ -39,6 +39,8 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 
 // conv3x3.cu: halo-tile kernel for 3x3 stride-1 convs; CAL_E_UNSUPPORTED = use the generic kernel
 int launch_conv3x3_halo(const CalConvArgs* a, void* stream);
+// Programmatic dependent launch between the path's own kernels (opt-in: CAL_PDL=1).
+bool pdl_enabled();
 
 // ----------------------------------------------------------------------------- device
 #ifdef __CUDACC__
@@ -187,6 +189,26 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start (prologue: barrier init, TMEM allocation, constant weights) while its
+// predecessor in the stream drains; griddep_wait() returns once the predecessor grid has completed
+// and its writes are visible - every access to activations goes after it.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// The same with both operand descriptors given as their low words (start address, LBO) over a
+// shared high word (SBO, version, swizzle mode): the issue loop then carries 32-bit adds only.
+__device__ __forceinline__ void umma_f16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // mbarrier arrives when all previously issued tcgen05.mma of this thread complete

@@ -31,7 +31,7 @@ namespace {
 constexpr int H_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 constexpr int H_EPI_THREADS = 256;
 constexpr int H_MAX_A_STAGES = 4;
-constexpr int H_MAX_B_STAGES = 8;
+constexpr int H_MAX_B_STAGES = 12;
 constexpr int H_TMEM_COLS = 512;
 constexpr int H_MAX_ACC = 8;              // TMEM accumulator stages (512 columns / N_tile)
 constexpr int H_MAX_BIAS = 1024;
@@ -41,18 +41,22 @@ struct HaloParams {
   int B, H, W, Cout_pad;
   int TWp, TW, R;
   int cluster, part_rows, n_slowest;   // weight slices multicast over `cluster` CTAs, part_rows rows loaded by each
-  int dual, RI;            // dual: a work item is two vertically adjacent tiles sharing every weight slice; RI = rows per item
+  int T, RI;               // a work item is T (1, 2 or 4) vertically adjacent tiles sharing every weight slice; RI = T*R rows
   int tiles_x, tiles_y, n_tiles, total_tiles;
   int N_tile, mma_n, nblk, ncc;
   int ksteps_last;         // K = 16 steps of the last 64-channel chunk that hold real channels
   int n_acc, acc_stride;   // accumulator ring in TMEM: n_acc stages of acc_stride columns
+  int w_slices;            // weights are slice-major: slice s = rows [s*Cout_rows, (s+1)*Cout_rows) of a (.., 64) matrix
+  int cout_rows;
   int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
   int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
   int w_resident, b_stages, b_slice_bytes;
+  int G, b_stage_bytes;    // streamed weights: a ring stage holds G consecutive (tap, chunk) slices
   uint32_t b_tx_bytes;
   const float* bias;
   const __half* res;
+  __half* yptr;            // output tensor (direct stores of the streamed-weight variant)
   long long* dbg;          // profiling experiments only: per-role clock64 stamps of CTA 0 (CAL_DEBUG_TIMELINE)
 };
 
@@ -99,7 +103,7 @@ __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool RESIDENT>
+template <bool RESIDENT, int T>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmBp, const __grid_constant__ CUtensorMap tmY,
@@ -108,7 +112,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = sA + p.a_stages * p.a_stage_bytes;
-  const int w_slots = RESIDENT ? 9 * p.ncc : p.b_stages;
+  const int w_slots = RESIDENT ? 9 * p.ncc : p.b_stages * p.G;
   uint8_t* sOut = sW + w_slots * p.b_slice_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + p.out_bufs * p.nblk * H_STAGE_BLOCK);
   uint64_t* fullA = bars;
@@ -122,6 +126,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.dbg && threadIdx.x == 0) {            // per-CTA wall-clock span (entries after the role stamps)
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[4 * 64 * 8 + 2 * blockIdx.x] = static_cast<long long>(gt);
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -130,7 +139,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], p.cluster); }
     mbar_init(wfull, 1);
-    for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], p.dual ? 8 : 4); }
+    for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], T > 1 ? 4 * T : 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, H_TMEM_COLS);
@@ -140,6 +149,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (p.cluster > 1) cluster_sync_all();      // peers' barriers are initialised before any multicast reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();                 // the next kernel's prologue may overlap this kernel's tail
+  const int items_cta = (p.total_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   const uint32_t crank = p.cluster > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = static_cast<uint16_t>((1u << p.cluster) - 1u);
 
@@ -148,10 +159,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       if (RESIDENT) {
         mbar_expect_tx(wfull, p.b_tx_bytes * 9u * static_cast<uint32_t>(p.ncc));
-        for (int s = 0; s < 9 * p.ncc; ++s) tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
+        for (int s = 0; s < 9 * p.ncc; ++s) {
+          if (p.w_slices) tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, 0, s * p.cout_rows);
+          else tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
+        }
       }
-      int sa = 0, sb = 0;
+      griddep_wait();                           // activations of the previous kernel from here on
+      int sa = 0, sb = 0, g = 0;
       uint32_t pha = 0, phb = 0;
+      int slices_left = items_cta * 9 * p.ncc;   // of this CTA, over all its items
       HTileIter ti;
       ti.init(p, blockIdx.x, gridDim.x);
       int pi = 0;
@@ -169,15 +185,33 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
           if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           if (!RESIDENT) {
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&emptyB[sb], phb ^ 1);           // freed by every CTA of the cluster
-              mbar_expect_tx(&fullB[sb], p.b_tx_bytes);
-              if (p.cluster > 1)                         // this CTA's rows of the slice, to all peers
-                tma_load_2d_mcast(sW + sb * p.b_slice_bytes + crank * p.part_rows * 128, &tmBp, &fullB[sb],
-                                  (tap * p.ncc + cc) * 64, tc.n0 + static_cast<int>(crank) * p.part_rows, cmask);
-              else
-                tma_load_2d(sW + sb * p.b_slice_bytes, &tmB, &fullB[sb], (tap * p.ncc + cc) * 64, tc.n0);
-              if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            // Weight slices go G to a ring stage (one barrier pair per stage: the MMA issuer pays
+            // ~400 cycles per wait + commit); stages run through tile and chunk boundaries, only
+            // the CTA's last one may be short.
+            for (int t9 = 0; t9 < 9; ++t9) {
+              if (g == 0) {
+                if (cc == 0 && t9 == 3) H_STAMP(0, pi, 2);
+                mbar_wait(&emptyB[sb], phb ^ 1);         // freed by every CTA of the cluster
+                if (cc == 0 && t9 == 3) H_STAMP(0, pi, 3);
+                const int n = slices_left < p.G ? slices_left : p.G;
+                if (!(p.ablate & 16)) mbar_expect_tx(&fullB[sb], n * p.b_tx_bytes);
+              }
+              uint8_t* dst = sW + sb * p.b_stage_bytes + g * p.b_slice_bytes;
+              const int sl = t9 * p.ncc + cc;
+              const int kx = p.w_slices ? 0 : sl * 64, ry = p.w_slices ? sl * p.cout_rows + tc.n0 : tc.n0;
+              if (p.ablate & 16) {
+              } else if (p.cluster > 1) {                // this CTA's rows of the slice, to all peers
+                tma_load_2d_mcast(dst + crank * p.part_rows * 128, &tmBp, &fullB[sb], kx,
+                                  ry + static_cast<int>(crank) * p.part_rows, cmask);
+              } else {
+                tma_load_2d(dst, &tmB, &fullB[sb], kx, ry);
+              }
+              --slices_left;
+              if (++g == p.G || slices_left == 0) {
+                if (p.ablate & 16) mbar_arrive(&fullB[sb]);
+                g = 0;
+                if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+              }
             }
           }
         }
@@ -185,82 +219,100 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    // The whole warp walks the (warp-uniform) schedule and one elected lane issues, so the
-    // descriptors live in uniform registers; per MMA only a 32-bit add on the descriptor's
-    // address field remains (N is 48..192 here: an MMA retires every 24..96 cycles, so the
-    // issue loop has to be a handful of instructions per MMA).
+    // The whole warp walks the (warp-uniform) schedule and one elected lane issues. N is 48..192
+    // here, an MMA retires every 44..96 cycles and the tensor pipe queues only a couple of them
+    // (tools/gpu_mma_rate.py), so the loop between two MMAs has to be a handful of instructions:
+    // everything is hoisted into registers, the descriptors advance by 32-bit adds on their low
+    // word, the tap order and the tiles per item are compile-time constants.
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
     const uint32_t idesc = make_idesc_f16(128, p.mma_n);
     const uint64_t desc0 = make_smem_desc(0, 128, 2);      // everything but the start address
+    const uint32_t dhi = static_cast<uint32_t>(desc0 >> 32), dlo = static_cast<uint32_t>(desc0);
     uint32_t tap_off[9];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(((tap / 3) * p.TWp + (tap % 3)) * 128) >> 4;
     const bool issuer = elect_one();
+    const bool do_mma = issuer && !(p.ablate & 4);
+    const bool mc = p.cluster > 1;
+    const bool stamp = p.dbg != nullptr && issuer;
     if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
-    const uint32_t w0 = (smem_u32(sW) & 0x3FFFF) >> 4, w_tap = static_cast<uint32_t>(p.ncc * p.b_slice_bytes) >> 4,
-                   w_cc = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
+    const uint32_t a_lo0 = dlo + ((smem_u32(sA) & 0x3FFFF) >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
+    const uint32_t w_lo0 = dlo + ((smem_u32(sW) & 0x3FFFF) >> 4), w_step = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
+    const uint32_t w_tap = static_cast<uint32_t>(p.ncc) * w_step;
+    const uint32_t a_tile1 = static_cast<uint32_t>(p.R * p.TWp * 128) >> 4;   // next tile of the item: R image rows down
+    const uint32_t acc_stride = p.acc_stride;
+    const int ncc = p.ncc, n_acc = p.n_acc, a_stages = p.a_stages, b_stages = p.b_stages, ksteps_last = p.ksteps_last;
+    const int step = gridDim.x, total = p.total_tiles;
+    uint32_t a_lo = a_lo0, b_lo = w_lo0;                    // low descriptor words of stages sa / sb
+    const int G = p.G;
+    const uint32_t b_stage_step = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+    int g = 0, slices_left = items_cta * 9 * ncc;           // position in the weight stage; slices this CTA still consumes
+    bool b_ready = false;                                   // the current weight stage was already waited for
     int mi = 0;
     bool pre = false;        // this item's tempty / first fullA were already waited for (see below)
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++mi) {
-      if (issuer) H_STAMP(1, mi, 0);
-      const bool has_next = t + static_cast<int>(gridDim.x) < p.total_tiles;
+    for (int t = blockIdx.x; t < total; t += step, ++mi) {
+      if (stamp) H_STAMP(1, mi, 0);
+      const bool has_next = t + step < total;
       bool pre_next = false;
       if (!pre) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
       }
-      if (issuer) H_STAMP(1, mi, 1);
-      const uint32_t d_tmem = tmem_base + as * (p.dual ? 2 * p.acc_stride : p.acc_stride);
-      const uint32_t d_tmem1 = d_tmem + p.acc_stride;          // second tile of a dual item
-      const uint32_t a_tile1 = static_cast<uint32_t>(p.R * p.TWp * 128) >> 4;
-      for (int cc = 0; cc < p.ncc; ++cc) {
+      if (stamp) H_STAMP(1, mi, 1);
+      const uint32_t d_tmem = tmem_base + as * (T * acc_stride);
+      for (int cc = 0; cc < ncc; ++cc) {
         if (!(pre && cc == 0)) {
           mbar_wait(&fullA[sa], pha);
           tc_fence_after();
         }
-        if (issuer) H_STAMP(1, mi, 2);
-        const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + sa * p.a_stage_bytes) & 0x3FFFF) >> 4);
-        const int nk = (cc == p.ncc - 1) ? p.ksteps_last : 4;     // pad lanes of the last chunk are zero: skip them
+        if (stamp) H_STAMP(1, mi, 2);
+        const int nk = (cc == ncc - 1) ? ksteps_last : 4;       // pad lanes of the last chunk are zero: skip them
+        const uint32_t w_cc = w_lo0 + cc * w_step;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          uint64_t b0;
-          if (RESIDENT) {
-            b0 = desc0 | static_cast<uint64_t>(w0 + tap * w_tap + cc * w_cc);
-          } else {
-            mbar_wait(&fullB[sb], phb);
-            tc_fence_after();
-            b0 = desc0 | static_cast<uint64_t>((smem_u32(sW + sb * p.b_slice_bytes) & 0x3FFFF) >> 4);
-          }
-          if (issuer && !(p.ablate & 4)) {
-            const uint64_t at = a0 + tap_off[tap];
-            umma_f16(d_tmem, at, b0, idesc, (cc | tap) != 0);
-            if (nk > 1) umma_f16(d_tmem, at + 2, b0 + 2, idesc, 1);
-            if (nk > 2) umma_f16(d_tmem, at + 4, b0 + 4, idesc, 1);
-            if (nk > 3) umma_f16(d_tmem, at + 6, b0 + 6, idesc, 1);
-            if (p.dual) {
-              const uint64_t at1 = at + a_tile1;
-              umma_f16(d_tmem1, at1, b0, idesc, (cc | tap) != 0);
-              if (nk > 1) umma_f16(d_tmem1, at1 + 2, b0 + 2, idesc, 1);
-              if (nk > 2) umma_f16(d_tmem1, at1 + 4, b0 + 4, idesc, 1);
-              if (nk > 3) umma_f16(d_tmem1, at1 + 6, b0 + 6, idesc, 1);
+        for (int t9 = 0; t9 < 9; ++t9) {
+          if (!RESIDENT && g == 0 && !b_ready) mbar_wait(&fullB[sb], phb);
+          if (do_mma) {
+            const uint32_t at = a_lo + tap_off[t9];
+            const uint32_t bl = RESIDENT ? w_cc + t9 * w_tap : b_lo + g * w_step;
+            const uint32_t first = (cc | t9) != 0;
+#pragma unroll
+            for (int tl = 0; tl < T; ++tl) {                 // the tiles of the item share the slice
+              const uint32_t al = at + tl * a_tile1;
+              const uint32_t dt = d_tmem + tl * acc_stride;
+              umma_f16_lo(dt, al, bl, dhi, idesc, first);
+              if (nk > 1) umma_f16_lo(dt, al + 2, bl + 2, dhi, idesc, 1);
+              if (nk > 2) umma_f16_lo(dt, al + 4, bl + 4, dhi, idesc, 1);
+              if (nk > 3) umma_f16_lo(dt, al + 6, bl + 6, dhi, idesc, 1);
             }
-            if (!RESIDENT) { if (p.cluster > 1) umma_commit_mcast(&emptyB[sb], cmask); else umma_commit(&emptyB[sb]); }
-          } else if (issuer && !RESIDENT) {
-            if (p.cluster > 1) umma_commit_mcast(&emptyB[sb], cmask); else umma_commit(&emptyB[sb]);
           }
-          __syncwarp();
           if (!RESIDENT) {
-            if (++sb == p.b_stages) { sb = 0; phb ^= 1; }
+            --slices_left;
+            if (g == G - 1 || slices_left == 0) {
+              // End of a ring stage. A shared-memory access of this thread right after its own
+              // tcgen05.commit stalls ~230 cycles and the tensor pipe queues only a couple of MMAs
+              // (tools/gpu_mma_rate.py), so the wait for the NEXT stage goes first, while this
+              // stage's MMAs are still queued, and the commit after it.
+              const int sb_n = (sb + 1 == b_stages) ? 0 : sb + 1;
+              const uint32_t ph_n = (sb_n == 0) ? (phb ^ 1) : phb;
+              b_ready = slices_left != 0;
+              if (b_ready) mbar_wait(&fullB[sb_n], ph_n);
+              if (issuer) { if (mc) umma_commit_mcast(&emptyB[sb], cmask); else umma_commit(&emptyB[sb]); }
+              __syncwarp();
+              sb = sb_n; phb = ph_n; g = 0;
+              b_lo = w_lo0 + sb * b_stage_step;
+            } else {
+              ++g;
+            }
           }
-          if (RESIDENT && tap == 5 && cc == p.ncc - 1 && has_next) {
+          if (RESIDENT && t9 == 5 && cc == ncc - 1 && has_next) {
             // The MMA queue still holds this item's last taps: take the next item's barrier
             // waits (accumulator stage free, first operand tile landed) off the tensor pipe's
             // critical path.
-            const int as_n = (as + 1 == p.n_acc) ? 0 : as + 1;
+            const int as_n = (as + 1 == n_acc) ? 0 : as + 1;
             const uint32_t aph_n = (as_n == 0) ? (aphase ^ 1) : aphase;
             mbar_wait(&tempty[as_n], aph_n ^ 1);
-            const int sa_n = (sa + 1 == p.a_stages) ? 0 : sa + 1;
+            const int sa_n = (sa + 1 == a_stages) ? 0 : sa + 1;
             const uint32_t pha_n = (sa_n == 0) ? (pha ^ 1) : pha;
             mbar_wait(&fullA[sa_n], pha_n);
             tc_fence_after();
@@ -269,12 +321,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (issuer) umma_commit(&emptyA[sa]);
         __syncwarp();
-        if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
+        a_lo += a_step;
+        if (++sa == a_stages) { sa = 0; pha ^= 1; a_lo = a_lo0; }
       }
       if (issuer) umma_commit(&tfull[as]);
-      if (issuer) H_STAMP(1, mi, 3);
+      if (stamp) H_STAMP(1, mi, 3);
       __syncwarp();
-      if (++as == p.n_acc) { as = 0; aphase ^= 1; }
+      if (++as == n_acc) { as = 0; aphase ^= 1; }
       pre = pre_next;
     }
   } else {
@@ -282,6 +335,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // Two groups of four warps ping-pong over the tiles: group g owns TMEM accumulator stage g
     // and staging buffer g, so the latency chain of one tile's epilogue (TMEM load, residual
     // read, staging, store issue) overlaps the other group's.
+    griddep_wait();                             // residual reads and output writes follow the previous kernel
     const int quarter = warp & 3;
     const int grp = (warp - 2) >> 2;
     const int groups_total = p.N_tile >> 5;                 // 32-column groups
@@ -290,26 +344,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ms = r * p.TW + xx;                            // row of this pixel in the dense R x TW staging tile
     const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
     uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
-    const bool prefetch_res = (p.res != nullptr) && groups_total <= 2;
+    const bool prefetch_res = (p.res != nullptr) && groups_total <= 2 && T <= 2;
     // residual rows are fetched one of this group's tiles ahead (the accumulator ring lets the
     // MMAs run far ahead, so nothing else would hide the read latency)
     uint4 rnext[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
-    // single mode: the groups alternate over the items; dual mode: group g takes tile g of every item
-    const int t_start = blockIdx.x + (p.dual ? 0 : grp * gridDim.x);
-    const int t_step = (p.dual ? 1 : 2) * gridDim.x;
-    const int as_step = p.dual ? 1 : 2;
-    const int yoff = p.dual ? grp * p.R : 0;
-    const uint32_t col_off = p.dual ? grp * p.acc_stride : 0;
-    const uint32_t item_cols = p.dual ? 2 * p.acc_stride : p.acc_stride;
+    // single mode: the groups alternate over the items; multi-tile items: group g takes tiles g, g+2 of every item
+    constexpr bool multi = T > 1;
+    constexpr int subs = multi ? T / 2 : 1;          // tiles of an item handled by this group
+    const int t_start = blockIdx.x + (multi ? 0 : grp * gridDim.x);
+    const int t_step = (multi ? 1 : 2) * gridDim.x;
+    const int as_step = multi ? 1 : 2;
+    const uint32_t item_cols = T * p.acc_stride;
     HTileIter ti, tn;                       // this group's current item and the one after it
     ti.init(p, t_start, t_step);
     tn = ti;
     auto residual_row = [&](int t, const HTileIter& itr) -> const __half* {
       if (t >= p.total_tiles) return nullptr;
       const HTile c = itr.get(p);
-      const int yy = c.y0 + yoff + r, xq = c.x0 + xx;
+      const int yy = c.y0 + (multi ? grp * p.R : 0) + r, xq = c.x0 + xx;
       if (!((xx < p.TW) && (yy < p.H) && (xq < p.W))) return nullptr;
       return p.res + ((static_cast<size_t>(c.b) * p.H + yy) * p.W + xq) * p.Cout_pad + c.n0;
     };
@@ -321,7 +375,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (q < groups_total * 4) rnext[q] = __ldg(reinterpret_cast<const uint4*>(r0) + q);
       }
     }
-    int as = p.dual ? 0 : grp;               // single mode: n_acc is even, this group sees stages grp, grp+2, ...
+    int as = multi ? 0 : grp;                // single mode: n_acc is even, this group sees stages grp, grp+2, ...
     uint32_t aphase = 0;
     int ei = 0;
     for (int t = t_start; t < p.total_tiles; t += t_step, ++ei) {
@@ -329,7 +383,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const HTile tc = ti.get(p);
       ti.advance(p);
       tn.advance(p);
-      const int ty0 = tc.y0 + yoff;
+      for (int sub = 0; sub < subs; ++sub) {
+      const int tl = multi ? grp + 2 * sub : 0;              // tile of the item this pass drains
+      const uint32_t col_off = tl * p.acc_stride;
+      const int ty0 = tc.y0 + tl * p.R;
       const int y = ty0 + r, x = tc.x0 + xx;
       const bool valid = (xx < p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tc.b) * p.H + y) * p.W + x;
@@ -349,18 +406,45 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       // this group's previous TMA stores must have finished reading its staging buffer
       if (leader) H_STAMP(2 + grp, ei, 1);
-      if (leader) bulk_wait_read();
-      if (leader) H_STAMP(2 + grp, ei, 2);
-      named_bar_sync(1 + grp, 128);
+      if (RESIDENT) {
+        if (leader) bulk_wait_read();
+        if (leader) H_STAMP(2 + grp, ei, 2);
+        named_bar_sync(1 + grp, 128);
+      }
       if (leader) H_STAMP(2 + grp, ei, 3);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       if (leader) H_STAMP(2 + grp, ei, 4);
       const uint32_t taddr = tmem_base + as * item_cols + col_off + (static_cast<uint32_t>(quarter * 32) << 16);
       // bias / residual / ReLU on one 32-column group and its 4 swizzled 16-byte staging writes
+      __half* yrow = p.yptr + pix * p.Cout_pad + tc.n0;
       auto finish_group = [&](const uint32_t (&acc)[32], const uint4 (&rq)[4], int g) {
-        if ((p.ablate & 2) || xx >= p.TW) return;            // halo columns are not staged
+        if ((p.ablate & 2) || xx >= p.TW) return;            // halo columns are not staged / stored
         const float* bb = s_bias + tc.n0 + g * 32;
+        if (!RESIDENT) {
+          // Streamed-weight layers: no staging tile - its shared memory buys a deeper weight ring,
+          // which is what bounds them - each lane writes its pixel's 32 channels as two full sectors.
+          if (!valid) return;
+          uint32_t o[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = q * 8 + 2 * j;
+              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+              float a = (g * 32 + c < p.mma_n) ? __uint_as_float(acc[c]) : 0.0f;
+              float b = (g * 32 + c + 1 < p.mma_n) ? __uint_as_float(acc[c + 1]) : 0.0f;
+              a += bb[c] + __low2float(rh);
+              b += bb[c + 1] + __high2float(rh);
+              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+              o[q * 4 + j] = h_pack_half2(a, b);
+            }
+          }
+          stg_v8(yrow + g * 32, o);
+          stg_v8(yrow + g * 32 + 16, o + 8);
+          return;
+        }
         uint8_t* blk = sStage + (g >> 1) * H_STAGE_BLOCK + ms * 128;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -410,10 +494,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
-      fence_proxy_async();                                // staging writes -> visible to the TMA unit
-      if (leader) H_STAMP(2 + grp, ei, 6);
-      named_bar_sync(1 + grp, 128);
-      if (leader && !(p.ablate & 1)) {
+      if (RESIDENT) {
+        fence_proxy_async();                              // staging writes -> visible to the TMA unit
+        if (leader) H_STAMP(2 + grp, ei, 6);
+        named_bar_sync(1 + grp, 128);
+      }
+      if (RESIDENT && leader && !(p.ablate & 1)) {
         // one store per 64-channel block: the R x TW box is dense in the staging tile; rows below
         // the image and columns right of it are clipped by the TMA unit
         if (ty0 < p.H)
@@ -422,6 +508,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bulk_commit();
       }
       if (leader) H_STAMP(2 + grp, ei, 7);
+      }
       as += as_step;
       if (as >= p.n_acc) { as -= p.n_acc; aphase ^= 1; }
     }
@@ -431,6 +518,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (p.cluster > 1) cluster_sync_all();      // no CTA leaves while a peer may still write into it
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg[4 * 64 * 8 + 2 * blockIdx.x + 1] = static_cast<long long>(gt);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, H_TMEM_COLS);
 }
 
@@ -454,11 +546,17 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   p.tiles_x = (a->Wout + p.TW - 1) / p.TW;
   int n_tiles = 1;
   while (a->Cout_pad % (64 * n_tiles) != 0 || a->Cout_pad / n_tiles > 256) ++n_tiles;
-  p.n_tiles = n_tiles;
-  p.N_tile = a->Cout_pad / n_tiles;
-  p.nblk = p.N_tile / 64;
-  int rows_left = a->Cout_rows;                       // weight rows available to the last N tile
-  p.mma_n = p.N_tile < rows_left ? p.N_tile : rows_left;
+  auto set_ntiles = [&](int nt) {
+    n_tiles = nt;
+    p.n_tiles = nt;
+    p.N_tile = a->Cout_pad / nt;
+    p.nblk = p.N_tile / 64;
+    p.mma_n = p.N_tile < a->Cout_rows ? p.N_tile : a->Cout_rows;   // weight rows of the (only) ragged N tile
+    p.acc_stride = (p.N_tile + 31) & ~31;
+    p.b_slice_bytes = ((p.mma_n * 128) + 1023) & ~1023;
+    p.b_tx_bytes = static_cast<uint32_t>(p.mma_n * 128);
+  };
+  set_ntiles(n_tiles);
   if (n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;   // ragged last N tile: generic kernel
   p.ncc = a->Cin_pad / 64;
   {
@@ -468,6 +566,8 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     if (p.ksteps_last > 4) p.ksteps_last = 4;
   }
   p.relu = a->relu;
+  p.w_slices = a->w_slices ? 1 : 0;
+  p.cout_rows = a->Cout_rows;
   { const char* e = getenv("CAL_DEBUG_ABLATE"); p.ablate = e ? atoi(e) : 0; }
   {
     // CAL_DEBUG_TIMELINE=<device pointer, hex>: 4 roles x 64 tiles x 8 stamps of long long
@@ -476,40 +576,78 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   }
   p.bias = a->bias;
   p.res = reinterpret_cast<const __half*>(a->res);
-  p.acc_stride = (p.N_tile + 31) & ~31;
-  // dual items (two tiles per weight slice: half the weight traffic, half the per-item handshakes)
-  // whenever two items of two accumulators each still fit the 512 TMEM columns
-  {
-    static const bool allow_dual = [] { const char* e = getenv("CAL_CONV_DUAL"); return !(e && e[0] == '0'); }();
-    p.dual = (allow_dual && 4 * p.acc_stride <= H_TMEM_COLS && a->Hout > p.R) ? 1 : 0;
-  }
-  p.RI = p.R * (1 + p.dual);
-  p.tiles_y = (a->Hout + p.RI - 1) / p.RI;
-  p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
-  p.a_stage_bytes = (p.RI + 2) * p.TWp * 128 + 1024;   // + pad rows read by the last taps of halo columns
-  p.a_tx_bytes = static_cast<uint32_t>((p.RI + 2) * p.TWp * 128);
-  p.b_slice_bytes = ((p.mma_n * 128) + 1023) & ~1023;
-  p.b_tx_bytes = static_cast<uint32_t>(p.mma_n * 128);
-  p.n_acc = H_TMEM_COLS / (p.acc_stride * (1 + p.dual));
-  if (p.n_acc > H_MAX_ACC) p.n_acc = H_MAX_ACC;
-  if (!p.dual) p.n_acc &= ~1;                         // single mode: stage parity == epilogue group
+  p.yptr = reinterpret_cast<__half*>(a->y);
+  // Work items of T vertically adjacent tiles share every weight slice (1/T of the weight traffic and,
+  // for streamed weights, of the per-slice barrier wait + commit of the MMA issuer). T = 2 whenever two
+  // items of two accumulators each fit the 512 TMEM columns, so the accumulator ring stays double
+  // buffered; measured on B200 (tools/gpu_ablate.py, batch 64): C=96 68x120 199 -> 133 us, while giving
+  // up the double buffering for T = 2 / 4 (C=192, 384; C=96 at T = 4) loses what the sharing gains.
+  // Resident weights share nothing but the handshakes, and with a residual input the two epilogue
+  // groups of a T = 2 item read their residual rows at the same moment: T = 1 there (178 vs 193 us).
   const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + H_MAX_BIAS * 4;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
-  // one staging buffer per epilogue group
-  p.out_bufs = 2;
-  const int budget = 224 * 1024 - 1024 - tail - 2 * p.nblk * H_STAGE_BLOCK;
-  if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget) {
+  const int budget_res = 224 * 1024 - 1024 - tail - 2 * p.nblk * H_STAGE_BLOCK;   // (evaluated before any N split)
+  const int budget_ring = 224 * 1024 - 1024 - tail;
+  auto set_tiles = [&](int T) {
+    p.T = T;
+    p.RI = p.R * T;
+    p.tiles_y = (a->Hout + p.RI - 1) / p.RI;
+    p.total_tiles = a->B * p.tiles_x * p.tiles_y * n_tiles;
+    p.a_stage_bytes = (p.RI + 2) * p.TWp * 128 + 1024;   // + pad rows read by the last taps of halo columns
+    p.a_tx_bytes = static_cast<uint32_t>((p.RI + 2) * p.TWp * 128);
+    p.n_acc = H_TMEM_COLS / (p.acc_stride * T);
+    if (p.n_acc > H_MAX_ACC) p.n_acc = H_MAX_ACC;
+    if (T == 1) p.n_acc &= ~1;                          // single mode: stage parity == epilogue group
+  };
+  static const int force_tiles = [] { const char* e = getenv("CAL_CONV_TILES"); return e ? atoi(e) : 0; }();   // experiments
+  const int max_tiles = force_tiles ? force_tiles : 2;
+  const bool fits2 = 4 * p.acc_stride <= H_TMEM_COLS && a->Hout > p.R;
+  set_tiles((max_tiles >= 2 && fits2 && (force_tiles || !a->res)) ? 2 : 1);
+  if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget_res) {
     p.w_resident = 1;
+    p.out_bufs = 2;
     p.b_stages = 0;
-    p.a_stages = (budget - w_all) / p.a_stage_bytes;
+    p.G = 1;
+    p.b_stage_bytes = p.b_slice_bytes;
+    p.a_stages = (budget_res - w_all) / p.a_stage_bytes;
   } else {
     p.w_resident = 0;
-    p.a_stages = 2;
-    p.b_stages = (budget - 2 * p.a_stage_bytes) / p.b_slice_bytes;
-    if (p.b_stages > H_MAX_B_STAGES) {
-      p.b_stages = H_MAX_B_STAGES;
-      p.a_stages = (budget - p.b_stages * p.b_slice_bytes) / p.a_stage_bytes;
+    p.out_bufs = 0;
+    // Experiment (CAL_CONV_NTILE_MAX=128): N tiles of at most 128 columns, so that T = 2 keeps a
+    // double-buffered accumulator ring (C = 192 -> 2 x 96, C = 384 -> 3 x 128) and the weight slices
+    // are read half as often per output. Measured on B200: C=192 34x60 97 us vs 86 us unsplit (the
+    // N = 96 MMAs run at 86 % of the N = 192 rate and the input patch is read twice), C=384 equal -
+    // so the default keeps the widest N tile.
+    static const int ntile_max = [] { const char* e = getenv("CAL_CONV_NTILE_MAX"); return e ? atoi(e) : 256; }();
+    if (a->Cout_rows == a->Cout_pad && p.N_tile > ntile_max) {
+      for (int nt = n_tiles; nt <= a->Cout_pad / 32; ++nt)
+        if (a->Cout_pad % nt == 0 && (a->Cout_pad / nt) % 32 == 0 && a->Cout_pad / nt <= ntile_max) { set_ntiles(nt); break; }
     }
+    const bool fits2s = 4 * p.acc_stride <= H_TMEM_COLS && a->Hout > p.R;
+    for (int T = 4; T >= 1; T >>= 1) {
+      if (T > max_tiles && T > 1) continue;
+      if (T > 1 && (T * p.acc_stride > H_TMEM_COLS || a->Hout <= p.R * (T / 2))) continue;
+      if (T > 1 && !force_tiles && !fits2s) continue;
+      set_tiles(T);
+      if (T == 1 || (budget_ring - 2 * p.a_stage_bytes) / p.b_slice_bytes >= 4) break;
+    }
+    // G slices per ring stage: as many as leave three stages next to two input patches
+    static const int force_g = [] { const char* e = getenv("CAL_CONV_G"); return e ? atoi(e) : 0; }();
+    p.a_stages = 2;
+    p.G = 1;
+    for (int G = 3; G >= 1; --G) {
+      if (force_g && G != force_g) continue;
+      const int st = (budget_ring - p.a_stages * p.a_stage_bytes) / (G * p.b_slice_bytes);
+      if (st >= 3 || G == 1 || force_g) { p.G = G; break; }
+    }
+    p.b_stage_bytes = p.G * p.b_slice_bytes;
+    // a third / fourth input patch while the ring keeps four stages
+    static const int want_a = [] { const char* e = getenv("CAL_A_STAGES"); return e ? atoi(e) : 4; }();
+    while (p.a_stages < want_a && p.a_stages < H_MAX_A_STAGES &&
+           (budget_ring - (p.a_stages + 1) * p.a_stage_bytes) / p.b_stage_bytes >= 4)
+      ++p.a_stages;
+    p.b_stages = (budget_ring - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+    if (p.b_stages > H_MAX_B_STAGES) p.b_stages = H_MAX_B_STAGES;
     if (p.b_stages < 2) return CAL_E_UNSUPPORTED;
   }
   if (p.a_stages > H_MAX_A_STAGES) p.a_stages = H_MAX_A_STAGES;
@@ -522,8 +660,11 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     int dev = 0;
     CAL_CHECK_CUDA(cudaGetDevice(&dev));
     CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (!p.w_resident) {
@@ -537,7 +678,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
       break;
     }
   }
-  const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages;
+  const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages * p.G;
   const size_t smem = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
                       static_cast<size_t>(w_slots) * p.b_slice_bytes + static_cast<size_t>(p.out_bufs) * p.nblk * H_STAGE_BLOCK + tail;
 
@@ -552,8 +693,10 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   }
   {
     const uint64_t ktot = 9ull * a->Cin_pad;
-    const uint64_t dims[2] = {ktot, (uint64_t)a->Cout_rows};
-    const uint64_t strides[1] = {ktot * 2};
+    // (rows, K) K-major matrix, or slice-major: (slices * rows, 64)
+    const uint64_t dims[2] = {a->w_slices ? 64ull : ktot,
+                              a->w_slices ? (ktot / 64) * (uint64_t)a->Cout_rows : (uint64_t)a->Cout_rows};
+    const uint64_t strides[1] = {a->w_slices ? 128ull : ktot * 2};
     const uint32_t box[2] = {64, (uint32_t)p.mma_n};
     int rc = encode_tmap_f16(&tmB, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
@@ -569,22 +712,33 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     int rc = encode_tmap_f16(&tmY, a->y, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
   }
+  {
+    static const bool show = getenv("CAL_DEBUG_CONFIG") != nullptr;
+    if (show)
+      fprintf(stderr, "halo conv %dx%d Cin_pad %d Cout_pad %d: N_tile %d G %d TWp %d R %d T %d resident %d a_stages %d b_stages %d "
+                      "slice %d B n_acc %d cluster %d smem %zu grid %d items %d\n",
+              a->Hout, a->Wout, a->Cin_pad, a->Cout_pad, p.N_tile, p.G, p.TWp, p.R, p.T, p.w_resident, p.a_stages, p.b_stages,
+              p.b_slice_bytes, p.n_acc, p.cluster, smem, grid, p.total_tiles);
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(H_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = static_cast<cudaStream_t>(stream);
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = p.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (p.w_resident)
-    CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true>, tmA, tmB, tmBp, tmY, p));
-  else
-    CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false>, tmA, tmB, tmBp, tmY, p));
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  if (p.w_resident && p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 2>, tmA, tmB, tmBp, tmY, p));
+  else if (p.w_resident) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1>, tmA, tmB, tmBp, tmY, p));
+  else if (p.T == 4) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 4>, tmA, tmB, tmBp, tmY, p));
+  else if (p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 2>, tmA, tmB, tmBp, tmY, p));
+  else CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 1>, tmA, tmB, tmBp, tmY, p));
   return CAL_OK;
 }
 

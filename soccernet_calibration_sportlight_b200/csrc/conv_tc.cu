@@ -402,6 +402,85 @@ __global__ void mn_mma_probe_kernel(const __grid_constant__ CUtensorMap tmX, con
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+// Experiment: issue rate of tcgen05.mma (M = 128, K = 16, kind::f16) from shared-memory operands
+// as a function of N and of the row alignment of the A operand's start address.
+__global__ void mma_rate_probe_kernel(int N, int shift_rows, int iters, int flags, long long* out) {
+  const int b_mn = flags & 1, fence_too = (flags >> 1) & 1, no_mma = (flags >> 2) & 1, commit_every = (flags >> 8) & 0xFF;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                       // 256 rows x 128 B
+  uint8_t* sB = smem + 256 * 128;           // 256 rows x 128 B
+  __shared__ uint64_t mbar, mbar2, mbar3;
+  __shared__ uint32_t tslot[2];
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) tslot[1] = 1u;
+  for (int i = threadIdx.x; i < 2 * 256 * 128 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&mbar, 1); mbar_init(&mbar2, 1u << 20); mbar_init(&mbar3, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tslot[0], 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tslot[0];
+  if (warp == 1) {
+    const bool issuer = elect_one();
+    const uint32_t idesc = make_idesc_f16(128, N) | (b_mn ? (1u << 16) : 0u);
+    const uint64_t a0 = make_smem_desc(smem_u32(sA) + shift_rows * 128, 128, 2);
+    const uint64_t b0 = b_mn ? make_smem_desc_ex(smem_u32(sB), 8192, 1024, 2) : make_smem_desc(smem_u32(sB), 128, 2);
+    long long t0 = 0, t1 = 0;
+    if (issuer) {
+      // warm-up, then a timed train of dependent-free MMAs into two alternating accumulators
+      for (int i = 0; i < 16; ++i) umma_f16(tmem_base, a0 + 2 * (i & 3), b0 + 2 * (i & 3), idesc, i != 0);
+      umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    if (issuer) {
+      t0 = clock64();
+      // groups of 4 MMAs (one 64-wide K slice) into two alternating accumulators; commit_every counts groups
+      const uint32_t kadv = b_mn ? 128 : 2;
+      const int cmask = commit_every ? commit_every - 1 : 0;      // power of two
+      for (int g = 0; g < iters / 4; ++g) {
+        const uint32_t d = tmem_base + (g & 1) * 256;
+        if (!no_mma) {
+          umma_f16(d, a0, b0, idesc, 1);
+          umma_f16(d, a0 + 2, b0 + kadv, idesc, 1);
+          umma_f16(d, a0 + 4, b0 + 2 * kadv, idesc, 1);
+          umma_f16(d, a0 + 6, b0 + 3 * kadv, idesc, 1);
+        }
+        if (commit_every && (g & cmask) == cmask) {
+          if ((flags & 64) && fence_too) mbar_wait(&mbar, 0);   // the wait BEFORE the commit
+          umma_commit(&mbar2);                               // never completes: 2^20 arrivals pending
+          if (flags & 64) continue;
+          if (fence_too) {
+            if (flags & 16) {                                // mbarrier.test_wait instead of try_wait
+              uint32_t ok = 0;
+              while (!ok)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+            } else if (flags & 32) {                         // a plain shared-memory flag poll
+              uint32_t v = 0;
+              while (!v) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&tslot[1])) : "memory");
+            } else {
+              mbar_wait(&mbar, 0);                           // an already-completed phase
+            }
+          }
+          if (flags & 8) tc_fence_after();
+        }
+      }
+      umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 1);
+    if (issuer) {
+      t1 = clock64();
+      out[blockIdx.x] = t1 - t0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
 int make_act_tmap(CUtensorMap* tm, const void* x, int B, int H, int W, int C, int box_w, int box_h,
                   int estride) {
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -437,6 +516,8 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
     CAL_REQUIRE(a->Cout_pad == 64 && a->n_classes >= 1 && a->n_classes <= a->Cout_rows && !a->res, CAL_E_UNSUPPORTED,
                 "cal_conv2d: softmax modes need Cout_pad == 64, n_classes <= Cout_rows, no residual");
 
+  CAL_REQUIRE(!a->w_slices || (a->ksize == 3 && a->stride == 1 && a->mode == 0), CAL_E_INVALID,
+              "cal_conv2d: slice-major weights are for 3x3 stride-1 convs");
   {
     // 3x3 stride-1 layers: halo-tile kernel (conv3x3.cu); CAL_CONV_HALO=0 forces the generic one
     static const bool use_halo = [] { const char* e = getenv("CAL_CONV_HALO"); return !(e && e[0] == '0'); }();
@@ -444,6 +525,7 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
       const int rc = launch_conv3x3_halo(a, stream);
       if (rc != CAL_E_UNSUPPORTED) return rc;
     }
+    CAL_REQUIRE(!a->w_slices, CAL_E_UNSUPPORTED, "cal_conv2d: shape needs the generic kernel, which takes K-major weights");
   }
   ConvParams p{};
   p.B = a->B; p.Hout = a->Hout; p.Wout = a->Wout; p.Cout_pad = a->Cout_pad;
@@ -568,6 +650,18 @@ extern "C" int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int 
   CAL_CHECK_CUDA(cudaFuncSetAttribute(mn_mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   mn_mma_probe_kernel<<<1, 128, 128 * 128 + 2 * 8192 + 1024, static_cast<cudaStream_t>(stream)>>>(tmX, tmY, mode,
                                                                                                   out_128x128);
+  CAL_CHECK_CUDA(cudaGetLastError());
+  return CAL_OK;
+}
+
+extern "C" int cal_debug_mma_rate(int N, int shift_rows, int iters, int flags, long long* out_cycles, void* stream) {
+  using namespace cal;
+  CAL_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && shift_rows >= 0 && shift_rows <= 64 && iters >= 1 && out_cycles,
+              CAL_E_INVALID, "cal_debug_mma_rate: bad args");
+  CAL_CHECK_CUDA(cudaFuncSetAttribute(mma_rate_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  const int grid = ((flags >> 16) & 0xFF) ? ((flags >> 16) & 0xFF) : 1;
+  mma_rate_probe_kernel<<<grid, 64, 2 * 256 * 128 + 1024, static_cast<cudaStream_t>(stream)>>>(N, shift_rows, iters, flags,
+                                                                                              out_cycles);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
 }

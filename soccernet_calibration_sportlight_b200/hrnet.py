@@ -265,7 +265,7 @@ def init_state_dict(cfg: Config, kind: str, seed: int = 0) -> "OrderedDict[str, 
 
 # ------------------------------------------------------------------------------- the engine
 class _Packed:
-    __slots__ = ("w", "b", "rows", "cin_pad", "cout_pad", "k", "s", "cin")
+    __slots__ = ("w", "b", "rows", "cin_pad", "cout_pad", "k", "s", "cin", "slices", "w_k")
 
 
 class HRNetHeatmap:
@@ -295,6 +295,9 @@ class HRNetHeatmap:
         self.training = False
         self.fused_head = os.environ.get("CAL_FUSED_HEAD", "1") != "0"
         self.chained_head = os.environ.get("CAL_HEAD_CHAIN", "1") != "0"
+        self.slice_major = os.environ.get("CAL_W_SLICES", "1") != "0"
+        self.branch_streams = os.environ.get("CAL_BRANCH_STREAMS", "0") != "0"   # measured neutral: off
+        self._streams: List[torch.cuda.Stream] = []
 
     # -- nn.Module-like surface used by the reference's callers
     def eval(self):
@@ -347,6 +350,11 @@ class HRNetHeatmap:
         p.w, p.b, p.rows = wp.to(self.device), bp.to(self.device), rows
         p.cin_pad, p.cout_pad, p.k, p.s = packing.pad_to(w.shape[1]), bp.numel(), k, s
         p.cin = int(w.shape[1])
+        # 3x3 stride-1 layers: slice-major weights (every (tap, 64-channel chunk) slice contiguous)
+        p.slices = bool(self.slice_major and k == 3 and s == 1)
+        p.w_k = p.w                       # K-major copy for the generic kernel (fallback shapes)
+        if p.slices:
+            p.w = p.w.reshape(p.rows, k * k * p.cin_pad // 64, 64).permute(1, 0, 2).contiguous()
         self._packed[key] = p
 
     def _pack(self):
@@ -392,6 +400,15 @@ class HRNetHeatmap:
         pad = p.k // 2
         Ho, Wo = (H + 2 * pad - p.k) // p.s + 1, (W + 2 * pad - p.k) // p.s + 1
         y = torch.empty((B, Ho, Wo, p.cout_pad), dtype=torch.float16, device=x.device)
+        if p.slices:
+            try:
+                return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res,
+                                  cin=p.cin, w_slices=True)
+            except ops._lib.CalError as e:
+                if "generic kernel" not in str(e):
+                    raise
+                p.slices = False            # this shape is served by the generic kernel: K-major from now on
+                p.w = p.w_k
         return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res, cin=p.cin)
 
     def _blocks(self, x, blocks):
@@ -405,7 +422,25 @@ class HRNetHeatmap:
 
     def _module(self, xs, module):
         branches, fuse = module
-        xs = [self._blocks(x, b) for x, b in zip(xs, branches)]
+        if self.branch_streams and len(xs) > 1:
+            # the branches of a module are independent until the fuse: one stream each, so the
+            # ramp-up / tail of one branch's (persistent) kernels is filled by another's
+            main = torch.cuda.current_stream(self.device)
+            while len(self._streams) < len(xs) - 1:
+                self._streams.append(torch.cuda.Stream(device=self.device))
+            outs_b = [None] * len(xs)
+            for i in range(1, len(xs)):
+                st = self._streams[i - 1]
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    outs_b[i] = self._blocks(xs[i], branches[i])
+            outs_b[0] = self._blocks(xs[0], branches[0])
+            for i in range(1, len(xs)):
+                main.wait_stream(self._streams[i - 1])
+                outs_b[i].record_stream(main)
+            xs = outs_b
+        else:
+            xs = [self._blocks(x, b) for x, b in zip(xs, branches)]
         nb = len(xs)
         outs = []
         for i in range(nb):

@@ -91,7 +91,7 @@ def line_decode(heat: torch.Tensor, sigma: float, scale: float = 1.0) -> torch.T
 
 def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: torch.Tensor, *,
            ksize: int, stride: int, cout_rows: int, relu: bool, res: Optional[torch.Tensor] = None,
-           mode: int = 0, n_classes: int = 0, cin: int = 0) -> torch.Tensor:
+           mode: int = 0, n_classes: int = 0, cin: int = 0, w_slices: bool = False) -> torch.Tensor:
     """x: fp16 NHWC (B,Hin,Win,Cin_pad); w: fp16 (Cout_rows, taps*Cin_pad);
     y: fp16 NHWC (B,Hout,Wout,Cout_pad) or fp32 NCHW (B,n_classes,Hout,Wout) for mode 1/2."""
     B, Hin, Win, Cin = x.shape
@@ -111,7 +111,10 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
         if ncls != n_classes:
             raise _lib.CalError("conv2d: n_classes mismatch")
         Cout_pad = 64
-    if w.shape[0] != cout_rows or w.shape[1] != ksize * ksize * Cin:
+    if w_slices:
+        if tuple(w.shape) != (ksize * ksize * Cin // 64, cout_rows, 64):
+            raise _lib.CalError(f"conv2d: slice-major weight shape {tuple(w.shape)}")
+    elif w.shape[0] != cout_rows or w.shape[1] != ksize * ksize * Cin:
         raise _lib.CalError(f"conv2d: weight shape {tuple(w.shape)} vs rows {cout_rows}, K {ksize * ksize * Cin}")
     if bias is not None and bias.numel() != Cout_pad:
         raise _lib.CalError("conv2d: bias length must equal Cout_pad")
@@ -119,6 +122,7 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
     a.Hout, a.Wout, a.Cout_pad, a.Cout_rows = Hout, Wout, Cout_pad, cout_rows
     a.ksize, a.stride, a.relu, a.mode, a.n_classes = ksize, stride, int(relu), mode, n_classes
     a.Cin = int(cin)                      # real channels: MMA K steps over the zero pad lanes are skipped
+    a.w_slices = int(bool(w_slices))
     name = "conv_tc" if PROFILE is None else f"conv_tc k{ksize}s{stride} {Cin}->{Cout_pad} @{Hout}x{Wout} m{mode}"
     with _Launch(name, x.device):
         st = _lib.lib().cal_conv2d(C.byref(a), _stream())

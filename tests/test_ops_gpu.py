@@ -32,9 +32,16 @@ def conv_case(B, H, W, ci, co, k, s, relu=True, res=False, mode=0, ncls=0, seed=
     if mode == 0:
         ref = F.relu(ref) if relu else ref
         y = torch.full((B, Ho, Wo, cop), float("nan"), dtype=torch.float16, device=dev)
-        ops.conv2d(xh, wp.to(dev), bp.to(dev), y, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16)
+        ops.conv2d(xh, wp.to(dev), bp.to(dev), y, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16, cin=ci)
         got = packing.from_nhwc16(y, co)
         assert bool((y[..., co:] == 0).all()), "channel padding lanes must be written as zero"
+        if k == 3 and s == 1:
+            # slice-major weights (every (tap, chunk) slice contiguous) must give the same bits
+            ws = wp.reshape(rows, -1, 64).permute(1, 0, 2).contiguous().to(dev)
+            y2 = torch.full_like(y, float("nan"))
+            ops.conv2d(xh, ws, bp.to(dev), y2, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16, cin=ci,
+                       w_slices=True)
+            assert torch.equal(y, y2)
         tol = 2e-3 * max(1.0, float(ref.abs().max())) + 1e-3
     else:
         ref = F.log_softmax(ref, 1) if mode == 1 else F.softmax(ref, 1)

@@ -12,12 +12,15 @@
 //     swizzle is a function of the absolute address; pinned by tools/gpu_shift_probe.py).
 //     Two of the TWp columns are halo: 6 % of the MMA rows compute values nobody stores.
 //   * weights stay resident in shared memory for the whole (persistent) CTA when they fit
-//     (C = 48 / 64), otherwise they stream through their own ring, one (tap, chunk) slice at a
-//     time;
+//     (C = 48 / 64), otherwise they stream through their own ring, G (tap, chunk) slices to a
+//     stage. The single MMA-issuing thread pays ~400 cycles per barrier wait + tcgen05.commit
+//     pair and the tensor pipe queues only a couple of MMAs (tools/gpu_mma_rate.py), so the issue
+//     loop is a handful of instructions per MMA, a stage's wait comes before the previous
+//     stage's commit, and work items of T = 2 tiles share every slice where TMEM allows;
 //   * epilogue: TMEM -> registers (32 columns per tcgen05.ld) -> bias / residual / ReLU -> fp16
-//     into a swizzled staging tile -> TMA stores (one per image row and 64-channel block; the
-//     TMA unit clips the ragged right / bottom edges), so global writes are full 128-byte lines
-//     issued by the copy engine instead of 32-byte pieces from every thread.
+//     -> 32-byte-sector stores straight from registers (st.global.v8). A swizzled staging tile
+//     drained by TMA stores remains as a build option (-DCAL_HALO_STAGED): its shared-memory traffic
+//     competes with the MMA operand reads that bound the small-N layers.
 //
 // L2 -> SM traffic per tile drops from 9 x 16 KB (+ all weights) to 25 KB (+ nothing when the
 // weights are resident): the old per-tap kernel ran these layers at the L2 throughput cap.
@@ -36,6 +39,14 @@ constexpr int H_TMEM_COLS = 512;
 constexpr int H_MAX_ACC = 8;              // TMEM accumulator stages (512 columns / N_tile)
 constexpr int H_MAX_BIAS = 1024;
 constexpr int H_STAGE_BLOCK = 128 * 128;  // staging: 128 rows x 64 fp16 per channel block
+// The staged epilogue (swizzled staging tile drained by TMA stores) is compiled only with
+// -DCAL_HALO_STAGED: carrying both store paths costs the resident variants register spills, and the
+// direct path measured faster (see launch_conv3x3_halo).
+#ifdef CAL_HALO_STAGED
+constexpr bool H_STAGED_BUILD = true;
+#else
+constexpr bool H_STAGED_BUILD = false;
+#endif
 
 struct HaloParams {
   int B, H, W, Cout_pad;
@@ -351,6 +362,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
     for (int q = 0; q < 8; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
     // single mode: the groups alternate over the items; multi-tile items: group g takes tiles g, g+2 of every item
+    const bool staged = RESIDENT && H_STAGED_BUILD && p.out_bufs > 0;   // staging tile + TMA stores, or direct stores from registers
     constexpr bool multi = T > 1;
     constexpr int subs = multi ? T / 2 : 1;          // tiles of an item handled by this group
     const int t_start = blockIdx.x + (multi ? 0 : grp * gridDim.x);
@@ -406,7 +418,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       // this group's previous TMA stores must have finished reading its staging buffer
       if (leader) H_STAMP(2 + grp, ei, 1);
-      if (RESIDENT) {
+      if (staged) {
         if (leader) bulk_wait_read();
         if (leader) H_STAMP(2 + grp, ei, 2);
         named_bar_sync(1 + grp, 128);
@@ -421,7 +433,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       auto finish_group = [&](const uint32_t (&acc)[32], const uint4 (&rq)[4], int g) {
         if ((p.ablate & 2) || xx >= p.TW) return;            // halo columns are not staged / stored
         const float* bb = s_bias + tc.n0 + g * 32;
-        if (!RESIDENT) {
+        if (!staged) {
           // Streamed-weight layers: no staging tile - its shared memory buys a deeper weight ring,
           // which is what bounds them - each lane writes its pixel's 32 channels as two full sectors.
           if (!valid) return;
@@ -494,12 +506,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
-      if (RESIDENT) {
+      if (staged) {
         fence_proxy_async();                              // staging writes -> visible to the TMA unit
         if (leader) H_STAMP(2 + grp, ei, 6);
         named_bar_sync(1 + grp, 128);
       }
-      if (RESIDENT && leader && !(p.ablate & 1)) {
+      if (staged && leader && !(p.ablate & 1)) {
         // one store per 64-channel block: the R x TW box is dense in the staging tile; rows below
         // the image and columns right of it are clipped by the TMA unit
         if (ty0 < p.H)
@@ -586,7 +598,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   // groups of a T = 2 item read their residual rows at the same moment: T = 1 there (178 vs 193 us).
   const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + H_MAX_BIAS * 4;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
-  const int budget_res = 224 * 1024 - 1024 - tail - 2 * p.nblk * H_STAGE_BLOCK;   // (evaluated before any N split)
+  const int budget_res = 224 * 1024 - 1024 - tail - (H_STAGED_BUILD ? 2 * p.nblk * H_STAGE_BLOCK : 0);   // (evaluated before any N split)
   const int budget_ring = 224 * 1024 - 1024 - tail;
   auto set_tiles = [&](int T) {
     p.T = T;
@@ -605,7 +617,13 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   set_tiles((max_tiles >= 2 && fits2 && (force_tiles || !a->res)) ? 2 : 1);
   if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget_res) {
     p.w_resident = 1;
-    p.out_bufs = 2;
+    // Outputs go straight from registers to global memory (two full 32-byte sectors per lane and
+    // 32-channel group). The alternative - a swizzled staging tile drained by TMA stores,
+    // CAL_CONV_DIRECT=0 in a -DCAL_HALO_STAGED build - costs 32 KB of shared-memory traffic per tile next to the MMA operand
+    // reads, which are what bounds these small-N layers (an N = 48 MMA takes 32 + N/4 cycles of
+    // operand reads against N/2 of math): measured 217 -> 193 us with a residual, equal without.
+    static const bool direct = [] { const char* e = getenv("CAL_CONV_DIRECT"); return !H_STAGED_BUILD || !(e && e[0] == '0'); }();
+    p.out_bufs = direct ? 0 : 2;
     p.b_stages = 0;
     p.G = 1;
     p.b_stage_bytes = p.b_slice_bytes;

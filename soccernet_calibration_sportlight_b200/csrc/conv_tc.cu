@@ -42,6 +42,7 @@ struct ConvParams {
   int kc_per_tap, taps, stride, pad, num_k;
   int ksteps_last;   // K = 16 steps of the last channel chunk that hold real channels
   int relu, mode, n_classes;
+  int wait_ahead;    // MMA issuer: next stage's wait before this stage's commit (experiments: CAL_TC_WAIT_AHEAD=0)
   int stages, b_stage_bytes;
   int n_acc, acc_stride;
   uint32_t tx_bytes;
@@ -131,33 +132,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0, aphase = 0;
     const uint32_t idesc = make_idesc_f16(128, p.mma_n);
     const uint64_t desc0 = make_smem_desc(0, 128, 2);
+    const uint32_t dhi = static_cast<uint32_t>(desc0 >> 32), dlo = static_cast<uint32_t>(desc0);
+    const uint32_t a_lo0 = dlo + ((smem_u32(sA) & 0x3FFFF) >> 4), b_lo0 = dlo + ((smem_u32(sB) & 0x3FFFF) >> 4);
+    const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+    const int num_k = p.num_k, stages = p.stages, kc_per_tap = p.kc_per_tap, ksteps_last = p.ksteps_last, n_acc = p.n_acc;
     const bool issuer = elect_one();
+    bool ready = false;          // this stage's full barrier was already waited for
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * p.acc_stride;
       int cc_k = 0;
-      for (int k = 0; k < p.num_k; ++k) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint64_t a0 = desc0 | static_cast<uint64_t>((smem_u32(sA + stage * A_STAGE_BYTES) & 0x3FFFF) >> 4);
-        const uint64_t b0 = desc0 | static_cast<uint64_t>((smem_u32(sB + stage * p.b_stage_bytes) & 0x3FFFF) >> 4);
+      for (int k = 0; k < num_k; ++k) {
+        if (!ready) mbar_wait(&full[stage], phase);
+        const uint32_t a_lo = a_lo0 + stage * a_step, b_lo = b_lo0 + stage * b_step;
         if (issuer) {
           // +32 bytes per K=16 step inside the 128-byte swizzle span; steps over pad lanes skipped
-          const int nk = (cc_k == p.kc_per_tap - 1) ? p.ksteps_last : 4;
-          umma_f16(d_tmem, a0, b0, idesc, k != 0);
-          if (nk > 1) umma_f16(d_tmem, a0 + 2, b0 + 2, idesc, 1);
-          if (nk > 2) umma_f16(d_tmem, a0 + 4, b0 + 4, idesc, 1);
-          if (nk > 3) umma_f16(d_tmem, a0 + 6, b0 + 6, idesc, 1);
-          umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
+          const int nk = (cc_k == kc_per_tap - 1) ? ksteps_last : 4;
+          umma_f16_lo(d_tmem, a_lo, b_lo, dhi, idesc, k != 0);
+          if (nk > 1) umma_f16_lo(d_tmem, a_lo + 2, b_lo + 2, dhi, idesc, 1);
+          if (nk > 2) umma_f16_lo(d_tmem, a_lo + 4, b_lo + 4, dhi, idesc, 1);
+          if (nk > 3) umma_f16_lo(d_tmem, a_lo + 6, b_lo + 6, dhi, idesc, 1);
         }
+        const int sn = (stage + 1 == stages) ? 0 : stage + 1;
+        const uint32_t pn = (sn == 0) ? (phase ^ 1) : phase;
+        // A shared-memory access of this thread right behind its own tcgen05.commit stalls ~230
+        // cycles (tools/gpu_mma_rate.py): inside a tile the wait for the next stage goes before
+        // this stage's commit, while the MMAs just issued are still queued. (Not across tiles: the
+        // accumulator-complete commit must not wait for the next tile's loads.)
+        ready = p.wait_ahead && k + 1 < num_k;
+        if (ready) mbar_wait(&full[sn], pn);
+        if (issuer) umma_commit(&empty[stage]);   // frees the smem slot when these MMAs retire
         __syncwarp();
-        if (++cc_k == p.kc_per_tap) cc_k = 0;
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++cc_k == kc_per_tap) cc_k = 0;
+        stage = sn; phase = pn;
       }
       if (issuer) umma_commit(&tfull[as]);        // accumulator complete -> epilogue
       __syncwarp();
-      if (++as == p.n_acc) { as = 0; aphase ^= 1; }
+      if (++as == n_acc) { as = 0; aphase ^= 1; }
     }
   } else {
     // ---------------------------------------------------------------- epilogue
@@ -187,6 +199,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int q = 0; q < 8; ++q)
           if (q * 8 < p.N_tile) rpre[q] = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
       }
+      // wide tiles: the residual of column group g + 1 is in flight while group g is processed
+      // (and group 0's while the accumulator is still being computed)
+      uint4 rnext[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
+      if (!prefetch_res && rrow) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q * 8 < p.N_tile) rnext[q] = __ldg(reinterpret_cast<const uint4*>(rrow) + q);
+      }
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -199,11 +221,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int q = 0; q < 4; ++q) rq[q] = (g == 0) ? rpre[q] : rpre[4 + q];
           } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) rq[q] = make_uint4(0, 0, 0, 0);
-            if (rrow) {
+            for (int q = 0; q < 4; ++q) { rq[q] = rnext[q]; rnext[q] = make_uint4(0, 0, 0, 0); }
+            if (rrow && g + 1 < groups_total) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
-                if (g * 32 + q * 8 < p.N_tile) rq[q] = __ldg(reinterpret_cast<const uint4*>(rrow + g * 32) + q);
+                if ((g + 1) * 32 + q * 8 < p.N_tile) rnext[q] = __ldg(reinterpret_cast<const uint4*>(rrow + (g + 1) * 32) + q);
             }
           }
           uint32_t acc[32];
@@ -572,6 +594,7 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   CAL_REQUIRE(stages >= 2, CAL_E_UNSUPPORTED, "cal_conv2d: tile does not fit shared memory");
   p.stages = stages;
+  { static const bool wa = [] { const char* e = getenv("CAL_TC_WAIT_AHEAD"); return !(e && e[0] == '0'); }(); p.wait_ahead = wa ? 1 : 0; }
   p.tx_bytes = (uint32_t)(p.TW * p.TH * 128 + p.mma_n * 128);
   const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;
 

@@ -21,7 +21,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --
     python bench.py --workload $WL --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_under_ncu.txt 2>&1
 # full captures (one pass of the whole pipeline each; -s skips the warm-up pass): 3x3 halo convs of
 # stage 3/4, generic convs, the fused head, the fuse kernel, the decodes and the camera solve
-for spec in "halo:conv3x3_halo:420:6" "convtc:conv_tc_kernel:360:8" "head:head_fused:2:2" "combine:fuse_combine:40:3" \
+for spec in "halo:conv3x3_halo:420:6" "convtc:conv_tc_kernel:360:8" "head:head_:2:2" "combine:fuse_combine:40:3" \
             "decode:kp_decode:1:1" "linedecode:line_decode:1:1" "solve:camera_solve:1:1" "stem:stem_conv:2:1"; do
   IFS=: read name regex skip count <<< "$spec"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c $count -f -o $OUT/${TAG}_$name \

@@ -2,8 +2,8 @@
 //
 //  cal_stem_conv    : first 3x3/s2 conv 3->64 (+BN+ReLU) straight from the fp32 NCHW
 //                     frame (src/models/hrnet/hrnet.py:450-452).  Cin = 3 gives K = 27,
-//                     too thin for the tensor cores: CUDA-core direct conv, one output
-//                     pixel per thread, weights broadcast from shared memory.
+//                     too thin for the tensor cores: CUDA-core direct conv, two output
+//                     pixels per thread, weights broadcast from shared memory.
 //  cal_fuse_combine : y = [relu](bias + sum_i up_i(src_i)) over fp16 NHWC tensors, the
 //                     multi-resolution exchange of HighResolutionModule.forward
 //                     (hrnet.py:229-246) and the head's upsample (hrnet.py:489-509);
@@ -17,11 +17,17 @@ namespace {
 constexpr int STEM_CO = 64;
 constexpr int STEM_K = 27;
 
-__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x,
-                                                        const float* __restrict__ w,
-                                                        const float* __restrict__ bias,
-                                                        __half* __restrict__ y, int B, int H, int W,
-                                                        int Ho, int Wo) {
+// Two horizontally adjacent output pixels per thread: every weight quad read from shared memory
+// feeds eight FMAs instead of four (the kernel is bound by shared-memory weight reads + FMA issue,
+// not by HBM), and a 256-thread block amortises its 7 KB weight load over 512 pixels. Per output the
+// FMA order is unchanged (k ascending), so results are bit-identical to the one-pixel version.
+constexpr int STEM_THREADS = 256;
+
+__global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const float* __restrict__ x,
+                                                                 const float* __restrict__ w,
+                                                                 const float* __restrict__ bias,
+                                                                 __half* __restrict__ y, int B, int H, int W,
+                                                                 int Ho, int Wo) {
   __shared__ __align__(16) float s_w[STEM_K * STEM_CO];   // [k][co]
   __shared__ __align__(16) float s_b[STEM_CO];
   for (int i = threadIdx.x; i < STEM_K * STEM_CO; i += blockDim.x) {
@@ -30,13 +36,16 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   }
   for (int i = threadIdx.x; i < STEM_CO; i += blockDim.x) s_b[i] = bias[i];
   __syncthreads();
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int ox = static_cast<int>(pix % Wo);
-  const int oy = static_cast<int>((pix / Wo) % Ho);
-  const int b = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
-  float in[STEM_K];
+  const int Wp = (Wo + 1) >> 1;                            // pixel pairs per output row
+  const long long total = static_cast<long long>(B) * Ho * Wp;
+  const long long pr = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (pr >= total) return;
+  const int ox = 2 * static_cast<int>(pr % Wp);
+  const int oy = static_cast<int>((pr / Wp) % Ho);
+  const int b = static_cast<int>(pr / (static_cast<long long>(Wp) * Ho));
+  const bool two = ox + 1 < Wo;
+  // input columns 2*ox-1 .. 2*ox+3 (the two pixels share column 2*ox+1), rows 2*oy-1 .. 2*oy+1
+  float in[3][3][5];
 #pragma unroll
   for (int ci = 0; ci < 3; ++ci) {
     const float* plane = x + (static_cast<size_t>(b) * 3 + ci) * H * W;
@@ -44,39 +53,52 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
+      for (int kx = 0; kx < 5; ++kx) {
         const int ix = 2 * ox + kx - 1;
         const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
-        in[ci * 9 + ky * 3 + kx] = ok ? __ldg(plane + static_cast<size_t>(iy) * W + ix) : 0.0f;
+        in[ci][ky][kx] = ok ? __ldg(plane + static_cast<size_t>(iy) * W + ix) : 0.0f;
       }
     }
   }
-  __half* out = y + static_cast<size_t>(pix) * STEM_CO;
+  __half* out = y + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * STEM_CO;
 #pragma unroll
   for (int c0 = 0; c0 < STEM_CO; c0 += 16) {
-    float acc[16];
+    float acc0[16], acc1[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = s_b[c0 + j];
+    for (int j = 0; j < 16; ++j) { acc0[j] = s_b[c0 + j]; acc1[j] = acc0[j]; }
 #pragma unroll
     for (int k = 0; k < STEM_K; ++k) {
+      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+      const float v0 = in[ci][ky][kx], v1 = in[ci][ky][kx + 2];
       const float4* wr = reinterpret_cast<const float4*>(s_w + k * STEM_CO + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 ww = wr[q];
-        acc[4 * q + 0] = fmaf(in[k], ww.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(in[k], ww.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(in[k], ww.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(in[k], ww.w, acc[4 * q + 3]);
+        acc0[4 * q + 0] = fmaf(v0, ww.x, acc0[4 * q + 0]);
+        acc0[4 * q + 1] = fmaf(v0, ww.y, acc0[4 * q + 1]);
+        acc0[4 * q + 2] = fmaf(v0, ww.z, acc0[4 * q + 2]);
+        acc0[4 * q + 3] = fmaf(v0, ww.w, acc0[4 * q + 3]);
+        acc1[4 * q + 0] = fmaf(v1, ww.x, acc1[4 * q + 0]);
+        acc1[4 * q + 1] = fmaf(v1, ww.y, acc1[4 * q + 1]);
+        acc1[4 * q + 2] = fmaf(v1, ww.z, acc1[4 * q + 2]);
+        acc1[4 * q + 3] = fmaf(v1, ww.w, acc1[4 * q + 3]);
       }
     }
     uint32_t o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      __half2 h = __floats2half2_rn(fmaxf(acc[2 * j], 0.0f), fmaxf(acc[2 * j + 1], 0.0f));
+      __half2 h = __floats2half2_rn(fmaxf(acc0[2 * j], 0.0f), fmaxf(acc0[2 * j + 1], 0.0f));
       o[j] = *reinterpret_cast<uint32_t*>(&h);
     }
-    *reinterpret_cast<uint4*>(out + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<uint4*>(out + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    stg_v8(out + c0, o);                                   // 16 channels = one full 32-byte sector
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        __half2 h = __floats2half2_rn(fmaxf(acc1[2 * j], 0.0f), fmaxf(acc1[2 * j + 1], 0.0f));
+        o[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      stg_v8(out + STEM_CO + c0, o);
+    }
   }
 }
 
@@ -199,8 +221,8 @@ extern "C" int cal_stem_conv(const float* x, const float* w, const float* bias, 
   CAL_REQUIRE(x && w && bias && y, CAL_E_INVALID, "cal_stem_conv: null pointer");
   CAL_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, CAL_E_INVALID,
               "cal_stem_conv: bad shape %dx%d -> %dx%d", H, W, Ho, Wo);
-  const long long total = static_cast<long long>(B) * Ho * Wo;
-  const int threads = 128;
+  const long long total = static_cast<long long>(B) * Ho * ((Wo + 1) / 2);     // pixel pairs
+  const int threads = STEM_THREADS;
   const long long blocks = (total + threads - 1) / threads;
   CAL_REQUIRE(blocks < (1ll << 31), CAL_E_UNSUPPORTED, "cal_stem_conv: too many pixels");
   stem_conv_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(

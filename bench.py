@@ -258,6 +258,16 @@ def run_b200(args, rank, world, local_rank):
                 r = sharding.all_gather_records(r, world * B).to("cpu")
             res_host = r
     e2e_run(2)
+    # the box's pinned host -> device rate on this batch (explains e2e when a box's PCIe path is slow:
+    # the copy of step i+1 overlaps step i only while it is shorter than the step)
+    hb0, hb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    hb0.record()
+    _tmp = host.to(dev, non_blocking=True)
+    hb1.record()
+    torch.cuda.synchronize()
+    h2d_ms = hb0.elapsed_time(hb1)
+    del _tmp
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -334,7 +344,8 @@ def run_b200(args, rank, world, local_rank):
                    "l2": "inputs larger than L2 (398 MB of frames + GBs of activations per step)",
                    "parallelism": f"frame shards x{world}, one NCCL all-gather of the results" if world > 1 else "single GPU"},
         "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "h2d_copy_ms_alone": h2d_ms, "h2d_gbps_alone": host.numel() * host.element_size() / h2d_ms / 1e6},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "decode": dec, "kernels_ms_per_step": kernels_ms,
     }
     if world == 1 and not args.no_cpu_baseline:

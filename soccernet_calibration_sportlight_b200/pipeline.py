@@ -31,6 +31,7 @@ class CalibrationPipeline:
         self.device = torch.device(device)
         self.two_streams = os.environ.get("CAL_TWO_STREAMS", "1") != "0"
         self._side = None
+        self._copy = None
         self.workload = workload
         self.size = (int(size[0]), int(size[1]))
         self.kp_model = metamodel.HRNetMetaModel({"nn_module": {"num_refinement_stages": 0},
@@ -94,27 +95,39 @@ class CalibrationPipeline:
         (``result_key`` defaults to 'cameras' when the solve is on, else 'keypoints').  This is the
         loop ``make_submit.py:59-73`` runs with the copies taken off the critical path."""
         key = result_key or ("cameras" if self.camera_creator is not None else "keypoints")
-        copy_stream = torch.cuda.Stream(device=self.device)
+        if self._copy is None:                      # one copy stream per pipeline (torch hands streams out of a small pool)
+            self._copy = torch.cuda.Stream(device=self.device)
+        copy_stream = self._copy
         compute = torch.cuda.current_stream(self.device)
         it = iter(host_batches)
+        # two device staging buffers, allocated once (no allocator traffic inside the loop): buffer k
+        # is refilled for batch i+2 only after batch i's kernels have consumed it
+        bufs, consumed = [None, None], [None, None]
 
-        def stage(h):
+        def stage(h, k):
             with torch.cuda.stream(copy_stream):
-                d = h.to(self.device, non_blocking=True)
+                if bufs[k] is None or bufs[k].shape != h.shape or bufs[k].dtype != h.dtype:
+                    bufs[k] = torch.empty(h.shape, dtype=h.dtype, device=self.device)
+                    bufs[k].record_stream(compute)
+                    consumed[k] = None
+                if consumed[k] is not None:
+                    copy_stream.wait_event(consumed[k])
+                bufs[k].copy_(h, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
-            return d, ev
+            return bufs[k], ev, k
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), 0)
         except StopIteration:
             return
         while nxt is not None:
-            cur, ev = nxt
+            cur, ev, k = nxt
             try:
-                nxt = stage(next(it))
+                nxt = stage(next(it), 1 - k)
             except StopIteration:
                 nxt = None
             compute.wait_event(ev)
             out = self(cur, keypoints_override=keypoints_override)
-            cur.record_stream(compute)
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(compute)
             yield out[key].to("cpu") if to_host else out[key]

@@ -189,8 +189,13 @@ int cal_camera_solve(const float* preds, const double* line_pts, const CalSolveP
 
 /* Single-camera helpers used by the Camera class mirror.
  * cal_pnp_refine  replaces Camera.refine_camera (baseline/camera.py:105-119);
- * cal_pnp_solve   replaces Camera.solve_pnp     (baseline/camera.py:92-103).
- *   obj (n,3) fp64, img (n,2) fp64, K (9) fp64 row-major, rvec/tvec (3) fp64 in/out */
+ * cal_pnp_solve   replaces Camera.solve_pnp     (baseline/camera.py:92-103), i.e. the pose
+ *                  cv2.solvePnPRansac(obj, img, K, None) returns: P3P on 4 matches, EPnP on 5,
+ *                  seeded 5-point RANSAC (8 px, 100 iterations, 0.99) + refit on the consensus set
+ *                  on more (csrc/solve_pnp_cv.cuh).  *ok = 1 reproduced; 0 OpenCV's RANSAC fails
+ *                  on these matches (the reference then reads uninitialised memory; rvec/tvec hold
+ *                  the least-squares pose); -1 no finite pose (rvec/tvec untouched).
+ *   obj (n,3) fp64, img (n,2) fp64, K (9) fp64 row-major, rvec/tvec (3) fp64 in/out; n <= 57 */
 int cal_pnp_refine(const double* obj, const double* img, int n, const double* K,
                    double* rvec, double* tvec, void* stream);
 int cal_pnp_solve(const double* obj, const double* img, int n, const double* K,

@@ -51,6 +51,12 @@ def plane_coords(plane: str, p: np.ndarray) -> np.ndarray:
 class CameraRef:
     """baseline/camera.py:77-426, the members the calibration path touches."""
 
+    # bookkeeping of this restatement only (golden-vector generation): when set, every
+    # refine_camera is repeated from its own result with a tight stopping rule; a result that still
+    # moves means OpenCV's LM stopped (step < 1e-5) before reaching a stationary point, so the
+    # reference's answer there is "where its solver happened to stop", not a minimiser
+    probe_convergence = False
+
     def __init__(self, iwidth=960, iheight=540):
         self.position = np.zeros(3)
         self.rotation = np.eye(3)
@@ -76,6 +82,7 @@ class CameraRef:
         # EPnP on random 5-point samples (OpenCV's internal RNG), and on the near-coplanar pitch
         # points that is often the flipped planar pose, which refine_camera then keeps.
         self.ransac = False
+        self.unconverged = False      # see probe_convergence
 
     # camera.py:92-103
     def solve_pnp(self, matches):
@@ -97,6 +104,12 @@ class CameraRef:
         img = np.array([m[1] for m in matches])
         crit = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 20000, 0.00001)
         rvec, t = cv2.solvePnPRefineLM(obj, img, self.calibration, None, rvec, -self.rotation @ self.position, crit)
+        if CameraRef.probe_convergence:
+            tight = (cv2.TERM_CRITERIA_MAX_ITER + cv2.TERM_CRITERIA_EPS, 200000, 1e-13)
+            r2, t2 = cv2.solvePnPRefineLM(obj, img, self.calibration, None, rvec.copy(), t.copy(), tight)
+            moved = max(float(np.abs(r2 - rvec).max()), float((np.abs(t2 - t) / np.maximum(np.abs(t), 1.0)).max()))
+            if not moved < 1e-6:
+                self.unconverged = True
         self.rotation, _ = cv2.Rodrigues(rvec)
         self.position = -self.rotation.T @ t
 
@@ -308,12 +321,14 @@ class CameraCreatorRef:
         self.pinned = True      # False when the outcome depended on a tainted camera (see CameraRef)
         self.minimal = False    # True when the outcome depended on OpenCV's 5-point EPnP shortcut
         self.ransac = False     # True when the outcome depended on any solvePnPRansac result
+        self.unconverged = False  # (CameraRef.probe_convergence) a refine_camera the outcome depended on stopped early
 
     def __call__(self, pred, name=None):
         self.branch = None
         self.pinned = True
         self.minimal = False
         self.ransac = False
+        self.unconverged = False
         try:
             return getattr(self, self.algorithm)(pred, name)
         except Exception:
@@ -368,6 +383,7 @@ class CameraCreatorRef:
                 self.branch = "multiplane"
                 if len(pts) > self.min_points_for_refinement:
                     cam.refine_camera(matched(pts))
+                    self.unconverged |= cam.unconverged
                     self.branch = "multiplane+refine"
                 return cam
         return None
@@ -394,15 +410,18 @@ class CameraCreatorRef:
                 self.pinned &= not cam.tainted
                 self.minimal |= cam.minimal
                 self.ransac |= cam.ransac
+                self.unconverged |= cam.unconverged
             if not feasible(cam.calibration, cam.position):
                 cam = None
             elif len(pts) > self.min_points_for_refinement:
                 cam.refine_camera(m)
+                self.unconverged |= cam.unconverged
                 self.branch += "+refine"
         if cam is None and hom is not None:
             self.pinned &= not hom[0].tainted
             self.minimal |= hom[0].minimal
             self.ransac |= hom[0].ransac
+            self.unconverged |= hom[0].unconverged
             if hom[1] < 26:
                 cam = hom[0]
                 self.branch = "ov_homography"
@@ -428,6 +447,7 @@ class CameraCreatorRef:
                 self.pinned &= not cand[0].tainted
                 self.minimal |= cand[0].minimal
                 self.ransac |= cand[0].ransac
+                self.unconverged |= cand[0].unconverged
             if cand is not None and feasible(cand[0].calibration, cand[0].position):
                 cams.append((cand[0], cand[1], tag))
         cam = None
@@ -440,6 +460,7 @@ class CameraCreatorRef:
             self.pinned &= not hom[0].tainted
             self.minimal |= hom[0].minimal
             self.ransac |= hom[0].ransac
+            self.unconverged |= hom[0].unconverged
             if hom[1] < self.max_rmse:
                 cam = hom[0]
                 self.branch = "voter_homography"

@@ -25,53 +25,60 @@ __global__ void __launch_bounds__(SOLVE_THREADS) camera_solve_kernel(const float
   solve::solve_frame(T, ws, P, fr, out + blockIdx.x);
 }
 
-// mode 0: refine from (rvec, tvec); mode 1: solve from scratch (planar initialisation)
+// mode 0: Camera.refine_camera - least squares from (rvec, tvec);
+// mode 1: Camera.solve_pnp - the cv2.solvePnPRansac restatement (solve_pnp_cv.cuh); *ok_out = 1 when
+// the reference's pose is reproduced, 0 when OpenCV's RANSAC fails on these matches (the reference
+// then holds uninitialised memory; the least-squares pose is returned)
 __global__ void __launch_bounds__(SOLVE_THREADS) pnp_kernel(const double* __restrict__ obj,
                                                             const double* __restrict__ img, int n,
                                                             const double* __restrict__ K, double* rvec,
                                                             double* tvec, int32_t* ok_out, int mode) {
   __shared__ solve::Workspace ws;
+  __shared__ solve::CamState cam;
   const solve::Team T{static_cast<int>(threadIdx.x), static_cast<int>(blockDim.x)};
-  if (T.tid == 0) {
-    ws.nobs = n; ws.nviews = 1; ws.use_f = 0; ws.guard = 1;
-    ws.fx = K[0]; ws.fy = K[4]; ws.cx = K[2]; ws.cy = K[5]; ws.f = K[0];
-    for (int k = 0; k < n; ++k) {
-      solve::Obs& o = ws.obs[k];
-      o.X = obj[3 * k]; o.Y = obj[3 * k + 1]; o.Z = obj[3 * k + 2];
-      o.u = img[2 * k]; o.v = img[2 * k + 1]; o.w = 1.0; o.view = 0;
-    }
-    if (mode == 0) {
+  if (mode == 0) {
+    if (T.tid == 0) {
+      ws.nobs = n; ws.nviews = 1; ws.use_f = 0; ws.guard = 1;
+      ws.fx = K[0]; ws.fy = K[4]; ws.cx = K[2]; ws.cy = K[5]; ws.f = K[0];
+      for (int k = 0; k < n; ++k) {
+        solve::Obs& o = ws.obs[k];
+        o.X = obj[3 * k]; o.Y = obj[3 * k + 1]; o.Z = obj[3 * k + 2];
+        o.u = img[2 * k]; o.v = img[2 * k + 1]; o.w = 1.0; o.view = 0;
+      }
       solve::rodrigues_to_R(rvec, ws.pose[0].R);
       for (int k = 0; k < 3; ++k) ws.pose[0].t[k] = tvec[k];
-    } else {
-      ws.hn = 0;
-      for (int k = 0; k < n && ws.hn < solve::NKP; ++k) {
-        if (fabs(obj[3 * k + 2]) > 1e-9) continue;
-        ws.hx[ws.hn] = obj[3 * k]; ws.hy[ws.hn] = obj[3 * k + 1];
-        ws.hu[ws.hn] = img[2 * k]; ws.hv[ws.hn] = img[2 * k + 1];
-        ++ws.hn;
-      }
     }
+    T.sync();
+    solve::lm_solve(T, ws, 100);
+    if (T.tid == 0) {
+      const bool fin = isfinite(ws.cost);
+      if (fin) {
+        solve::R_to_rodrigues(ws.pose[0].R, rvec);
+        for (int k = 0; k < 3; ++k) tvec[k] = ws.pose[0].t[k];
+      }
+      if (ok_out) *ok_out = fin ? 1 : 0;
+    }
+    return;
+  }
+  if (T.tid == 0) {
+    for (int k = 0; k < n; ++k) {
+      for (int j = 0; j < 3; ++j) ws.pnp_obj[3 * k + j] = static_cast<double>(static_cast<float>(obj[3 * k + j]));
+      for (int j = 0; j < 2; ++j) ws.pnp_px[2 * k + j] = static_cast<double>(static_cast<float>(img[2 * k + j]));
+    }
+    for (int k = 0; k < 9; ++k) { cam.K[k] = K[k]; cam.R[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+    cam.pos[0] = cam.pos[1] = cam.pos[2] = 0.0;
+    cam.ok = 1;
   }
   T.sync();
-  bool ok = true;
-  if (mode != 0) {
-    const bool enough = ws.hn >= 4;
-    T.sync();
-    ok = enough && solve::homography_fit(T, ws, nullptr, ws.H);
-    if (T.tid == 0) ws.flag = (ok && solve::pose_from_homography(ws.H, K[0], K[4], K[2], K[5], &ws.pose[0])) ? 1 : 0;
-    T.sync();
-    ok = ws.flag != 0;
-    T.sync();
-  }
-  if (ok) solve::lm_solve(T, ws, 100);
+  solve::solve_pnp_core(T, ws, n, &cam, false);
   if (T.tid == 0) {
-    const bool fin = ok && isfinite(ws.cost);
-    if (fin) {
-      solve::R_to_rodrigues(ws.pose[0].R, rvec);
-      for (int k = 0; k < 3; ++k) tvec[k] = ws.pose[0].t[k];
+    if (cam.ok) {
+      double t[3];
+      solve::mat3_vec(cam.R, cam.pos, t);
+      solve::R_to_rodrigues(cam.R, rvec);
+      for (int k = 0; k < 3; ++k) tvec[k] = -t[k];
     }
-    if (ok_out) *ok_out = fin ? 1 : 0;
+    if (ok_out) *ok_out = cam.ok ? (ws.pnp_status > 0 ? 1 : 0) : -1;
   }
 }
 
@@ -142,7 +149,7 @@ extern "C" int cal_pnp_solve(const double* obj, const double* img, int n, const 
                              double* tvec, int32_t* ok, void* stream) {
   using namespace cal;
   CAL_REQUIRE(obj && img && K && rvec && tvec, CAL_E_INVALID, "cal_pnp_solve: null pointer");
-  CAL_REQUIRE(n >= 4 && n <= solve::MAXOBS, CAL_E_INVALID, "cal_pnp_solve: n %d (4..%d)", n, solve::MAXOBS);
+  CAL_REQUIRE(n >= 4 && n <= solve::NKP, CAL_E_INVALID, "cal_pnp_solve: n %d (4..%d)", n, solve::NKP);
   pnp_kernel<<<1, SOLVE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(obj, img, n, K, rvec, tvec, ok, 1);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;

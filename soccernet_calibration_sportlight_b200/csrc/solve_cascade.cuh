@@ -5,6 +5,7 @@
 // the same path.
 #pragma once
 #include "solve_core.cuh"
+#include "solve_pnp_cv.cuh"
 
 namespace cal {
 namespace solve {
@@ -250,18 +251,158 @@ CAL_HD_NOINLINE inline void refine_camera(const Team& T, Workspace& ws, const Ca
   store_pose(T, ws, cam);
 }
 
-// Camera.solve_pnp (camera.py:92-103): the pose minimising the reprojection error of the matched
-// points for the camera's K.  Initial pose: the current one if `keep_init`, else the plane
-// homography of the matched ground-plane points (OpenCV's planar initialisation).
-CAL_HD_NOINLINE inline void solve_pnp(const Team& T, Workspace& ws, const CalSolveParams& P, const Points& pts, CamState* cam,
-                             bool keep_init) {
+// 6-DoF least squares over the matches flagged in `mask` (bit k = pts entry k), from the pose in *cam
+CAL_HD_NOINLINE inline void refine_camera_masked(const Team& T, Workspace& ws, int n, unsigned long long mask, CamState* cam) {
+  if (T.tid == 0) {
+    ws.nviews = 1; ws.use_f = 0; ws.guard = 1;
+    ws.fx = cam->K[0]; ws.fy = cam->K[4]; ws.cx = cam->K[2]; ws.cy = cam->K[5]; ws.f = cam->K[0];
+    int no = 0;
+    for (int k = 0; k < n; ++k) {
+      if (!((mask >> k) & 1ull)) continue;
+      Obs& o = ws.obs[no++];
+      o.X = ws.pnp_obj[3 * k]; o.Y = ws.pnp_obj[3 * k + 1]; o.Z = ws.pnp_obj[3 * k + 2];
+      o.u = ws.pnp_px[2 * k]; o.v = ws.pnp_px[2 * k + 1]; o.w = 1.0; o.view = 0;
+    }
+    ws.nobs = no;
+    for (int k = 0; k < 9; ++k) ws.pose[0].R[k] = cam->R[k];
+    mat3_vec(cam->R, cam->pos, ws.pose[0].t);
+    for (int k = 0; k < 3; ++k) ws.pose[0].t[k] = -ws.pose[0].t[k];
+  }
+  T.sync();
+  lm_solve(T, ws, 30);
+  store_pose(T, ws, cam);
+}
+
+CAL_HD inline void set_pose(CamState* cam, const double* R, const double* t) {
+  for (int k = 0; k < 9; ++k) cam->R[k] = R[k];
+  for (int i = 0; i < 3; ++i) cam->pos[i] = -(R[i] * t[0] + R[3 + i] * t[1] + R[6 + i] * t[2]);
+  bool fin = true;
+  for (int k = 0; k < 9; ++k) fin = fin && isfinite(R[k]);
+  for (int k = 0; k < 3; ++k) fin = fin && isfinite(cam->pos[k]);
+  if (!fin) cam->ok = 0;
+}
+
+// Camera.solve_pnp (camera.py:92-103) = cv2.solvePnPRansac(obj, img, K, None) with the result flag
+// ignored.  Restated in solve_pnp_cv.cuh; here the team-level driver:
+//   4 points -> P3P, 5 points -> EPnP (both by thread 0);
+//   more -> RANSAC: thread 0 draws every 5-point sample of the (at most 100) iterations from
+//   OpenCV's seeded generator, the team evaluates `nt` hypotheses at a time (EPnP + inlier count,
+//   one per thread), thread 0 replays OpenCV's sequential bookkeeping (best count, shrinking
+//   iteration budget) over them; then the iterative solver on the consensus set = least squares
+//   over the inliers from the winning sample's pose.
+// When the RANSAC fails (no sample reaches 5 inliers) the reference goes on with uninitialised
+// memory; nothing to reproduce - the least-squares pose over all matches is returned instead
+// (from the pose in *cam when `keep_init`, else from the ground-plane homography of the matches).
+// ws.pnp_status: 1 reproduced the reference's pose, 0 the RANSAC failed (fallback pose).
+// (the n matches are in ws.pnp_obj / ws.pnp_px, float32-rounded; K and the start pose in *cam)
+CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, CamState* cam, bool keep_init) {
+  if (T.tid == 0) {
+    ws.pnp_status = 0; ws.pnp_best = -1; ws.pnp_maxgood = 0; ws.pnp_niters = 100;
+    ws.pnp_mask = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+  }
+  T.sync();
+  double* hyp_pose = &ws.jac[0][0][0];                                   // 100 x 12
+  unsigned long long* hyp_mask = reinterpret_cast<unsigned long long*>(ws.hyp_err);
+  unsigned char* samples = reinterpret_cast<unsigned char*>(&ws.res[0][0]);   // 100 x 5
+  if (n == 4 || n == 5) {
+    if (T.tid == 0) {
+      double R[9], t[3];
+      bool ok;
+      if (n == 4) {
+        ok = cvx::p3p_4points(ws.pnp_obj, ws.pnp_px, cam->K, R, t);
+      } else {
+        double xn[10];
+        for (int k = 0; k < 5; ++k) {
+          xn[2 * k] = cvx::normalize_px(ws.pnp_px[2 * k], cam->K[2], cam->K[0]);
+          xn[2 * k + 1] = cvx::normalize_px(ws.pnp_px[2 * k + 1], cam->K[5], cam->K[4]);
+        }
+        cvx::Epnp5 e;
+        e.compute_pose(ws.pnp_obj, xn, cam->K, R, t);
+        ok = true;
+      }
+      if (ok) { set_pose(cam, R, t); ws.pnp_status = 1; }
+    }
+    T.sync();
+  } else if (n >= 6 && n <= NKP) {
+    if (T.tid == 0) {
+      cvx::CvRng rng(0xFFFFFFFFFFFFFFFFull);
+      for (int h = 0; h < 100; ++h)
+        for (int i = 0; i < 5; ++i) {
+          int v;
+          for (;;) {
+            v = rng.uniform(0, n);
+            bool dup = false;
+            for (int j = 0; j < i; ++j) dup = dup || samples[h * 5 + j] == v;
+            if (!dup) break;
+          }
+          samples[h * 5 + i] = (unsigned char)v;
+        }
+    }
+    T.sync();
+    for (int base = 0; base < 100; base += T.nt) {
+      const int budget = ws.pnp_niters;
+      T.sync();
+      if (base >= budget) break;
+      const int h = base + T.tid;
+      if (h < 100 && h < budget) {
+        double obj[15], xn[10], R[9], t[3];
+        for (int i = 0; i < 5; ++i) {
+          const int k = samples[h * 5 + i];
+          obj[3 * i] = ws.pnp_obj[3 * k]; obj[3 * i + 1] = ws.pnp_obj[3 * k + 1]; obj[3 * i + 2] = ws.pnp_obj[3 * k + 2];
+          xn[2 * i] = cvx::normalize_px(ws.pnp_px[2 * k], cam->K[2], cam->K[0]);
+          xn[2 * i + 1] = cvx::normalize_px(ws.pnp_px[2 * k + 1], cam->K[5], cam->K[4]);
+        }
+        cvx::Epnp5 e;
+        e.compute_pose(obj, xn, cam->K, R, t);
+        unsigned long long m = 0;
+        ws.hyp_cnt[h] = cvx::pnp_inliers(ws.pnp_obj, ws.pnp_px, n, cam->K, R, t, &m);
+        hyp_mask[h] = m;
+        for (int k = 0; k < 9; ++k) hyp_pose[h * 12 + k] = R[k];
+        for (int k = 0; k < 3; ++k) hyp_pose[h * 12 + 9 + k] = t[k];
+      }
+      T.sync();
+      if (T.tid == 0) {
+        for (int q = base; q < base + T.nt && q < 100 && q < ws.pnp_niters; ++q) {
+          const int good = ws.hyp_cnt[q];
+          if (good > (ws.pnp_maxgood > 4 ? ws.pnp_maxgood : 4)) {
+            ws.pnp_best = q; ws.pnp_maxgood = good;
+            ws.pnp_niters = cvx::update_num_iters(0.99, (double)(n - good) / n, 5, ws.pnp_niters);
+          }
+        }
+      }
+      T.sync();
+    }
+    const int best = ws.pnp_best;
+    T.sync();
+    if (best >= 0) {
+      // the iterative solver on the consensus set, started from the winning sample's pose
+      // (OpenCV 4.x hands the RANSAC model to the final solvePnP as its extrinsic guess: on the
+      // planar pitch the refit therefore stays in the basin - often the mirrored planar pose - that
+      // EPnP put the sample in)
+      if (T.tid == 0) {
+        ws.pnp_mask = hyp_mask[best];
+        ws.pnp_status = 1;
+        for (int k = 0; k < 12; ++k) ws.pnp_pose[k] = hyp_pose[best * 12 + k];
+        set_pose(cam, ws.pnp_pose, ws.pnp_pose + 9);
+      }
+      T.sync();
+      const bool ok = cam->ok != 0;
+      T.sync();
+      if (ok) refine_camera_masked(T, ws, n, ws.pnp_mask, cam);
+      return;
+    }
+  }
+  const bool reproduced = ws.pnp_status != 0;
+  T.sync();
+  if (reproduced && n <= 5) return;
+  // least squares over the consensus set (all matches when the RANSAC failed)
   if (!keep_init) {
     if (T.tid == 0) {
       ws.hn = 0;
-      for (int k = 0; k < pts.n; ++k) {
-        if (is_top(pts.id[k])) continue;
-        const double* w = P.pitch_xyz + 3 * pts.id[k];
-        ws.hx[ws.hn] = w[0]; ws.hy[ws.hn] = w[1]; ws.hu[ws.hn] = pts.x[k]; ws.hv[ws.hn] = pts.y[k];
+      for (int k = 0; k < n; ++k) {
+        if (ws.pnp_obj[3 * k + 2] != 0.0 || !((ws.pnp_mask >> k) & 1ull)) continue;     // ground-plane inliers
+        ws.hx[ws.hn] = ws.pnp_obj[3 * k]; ws.hy[ws.hn] = ws.pnp_obj[3 * k + 1];
+        ws.hu[ws.hn] = ws.pnp_px[2 * k]; ws.hv[ws.hn] = ws.pnp_px[2 * k + 1];
         ++ws.hn;
       }
     }
@@ -273,8 +414,9 @@ CAL_HD_NOINLINE inline void solve_pnp(const Team& T, Workspace& ws, const CalSol
       Pose p;
       const bool ok = fit && pose_from_homography(ws.H, cam->K[0], cam->K[4], cam->K[2], cam->K[5], &p);
       if (ok) {
-        for (int k = 0; k < 9; ++k) cam->R[k] = p.R[k];
-        for (int i = 0; i < 3; ++i) cam->pos[i] = -(p.R[i] * p.t[0] + p.R[3 + i] * p.t[1] + p.R[6 + i] * p.t[2]);
+        set_pose(cam, p.R, p.t);
+      } else if (ws.pnp_best >= 0) {
+        set_pose(cam, ws.pnp_pose, ws.pnp_pose + 9);
       } else {
         cam->ok = 0;
       }
@@ -283,7 +425,20 @@ CAL_HD_NOINLINE inline void solve_pnp(const Team& T, Workspace& ws, const CalSol
   }
   const bool ok = cam->ok != 0;
   T.sync();
-  if (ok) refine_camera(T, ws, P, pts, cam);
+  if (ok) refine_camera_masked(T, ws, n, ws.pnp_mask, cam);
+}
+
+CAL_HD inline void solve_pnp(const Team& T, Workspace& ws, const CalSolveParams& P, const Points& pts, CamState* cam,
+                             bool keep_init) {
+  if (T.tid == 0) {
+    for (int k = 0; k < pts.n; ++k) {
+      const double* w = P.pitch_xyz + 3 * pts.id[k];
+      ws.pnp_obj[3 * k] = f32r(w[0]); ws.pnp_obj[3 * k + 1] = f32r(w[1]); ws.pnp_obj[3 * k + 2] = f32r(w[2]);
+      ws.pnp_px[2 * k] = f32r(pts.x[k]); ws.pnp_px[2 * k + 1] = f32r(pts.y[k]);
+    }
+  }
+  T.sync();
+  solve_pnp_core(T, ws, pts.n, cam, keep_init);
 }
 
 // Camera.projection_rmse (camera.py:249-277): mean L2 distance; project_point rounds the
@@ -421,7 +576,10 @@ CAL_HD_NOINLINE inline void homography_camera(const Team& T, Workspace& ws, cons
   const bool ok = ws.hom.ok != 0;
   T.sync();
   if (!ok) return;
-  solve_pnp(T, ws, P, pts, &ws.hom, true);           // solve_pnp + refine_camera: one minimiser
+  solve_pnp(T, ws, P, pts, &ws.hom, true);
+  const bool pnp_ok = ws.hom.ok != 0;
+  T.sync();
+  if (pnp_ok) refine_camera(T, ws, P, pts, &ws.hom);
   const double r = projection_rmse(T, ws, P, pts, ws.hom);
   if (T.tid == 0) ws.hom_rmse = r;
   T.sync();
@@ -441,6 +599,9 @@ CAL_HD_NOINLINE inline double all_points_camera(const Team& T, Workspace& ws, co
   // pose of a ground-plane view 0 is the natural initial pose; a goal-plane view 0 lives in
   // swapped coordinates, so start from the ground homography instead.
   solve_pnp(T, ws, P, pts, &ws.cam, first_plane == 0);
+  const bool pnp_ok = ws.cam.ok != 0;
+  T.sync();
+  if (pnp_ok && pts.n > 6) refine_camera(T, ws, P, pts, &ws.cam);
   const bool ok = ws.cam.ok != 0;
   T.sync();
   if (!ok) return NAN;

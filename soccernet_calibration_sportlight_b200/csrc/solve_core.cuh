@@ -11,8 +11,8 @@
 //        (what the reference gets whenever its RANSAC succeeds and refines; when OpenCV's
 //        RANSAC fails the reference consumes uninitialised memory - not reproducible, see
 //        DESIGN.md);
-//   cv2.findHomography(RANSAC) -> deterministic 4-point hypotheses, consensus set, DLT on the
-//        inliers, LM polish;
+//   cv2.findHomography(RANSAC) -> OpenCV's seeded 4-point samples and sequential consensus
+//        bookkeeping (solve_pnp_cv.cuh), least squares on the consensus set;
 //   numpy SVD/Cholesky for K-from-homography (camera.py:366-426) -> one-sided Jacobi.
 // All arithmetic is fp64.  `Team` abstracts the thread block: on the device the parallel-for
 // loops stride over threadIdx.x and sync() is __syncthreads(); compiled for the host
@@ -43,7 +43,7 @@ constexpr int NKP = CAL_NUM_KEYPOINTS;   // 57
 constexpr int MAXV = 3;                  // planar views: ground plane, left goal, right goal
 constexpr int MAXOBS = 80;               // 53 + 10 + 10 observations at most
 constexpr int MAXP = 1 + 6 * MAXV;       // f + 3 poses
-constexpr int NHYP = 512;                // homography RANSAC hypotheses
+constexpr int NHYP = 512;                // RANSAC hypotheses evaluated per round (scratch size)
 
 struct Team {
   int tid, nt;
@@ -309,6 +309,12 @@ struct Workspace {
   int memo_n;
   unsigned long long hom_mask;
   int hom_memo_valid;
+  // solvePnPRansac restatement (solve_pnp_cv.cuh): float32-rounded matches, RANSAC state.  The
+  // hypotheses' samples, poses, inlier counts and masks live in res / jac / hyp_cnt / hyp_err,
+  // which are scratch between two least-squares solves.
+  double pnp_obj[NKP * 3], pnp_px[NKP * 2], pnp_pose[12];
+  unsigned long long pnp_mask;
+  int pnp_niters, pnp_best, pnp_maxgood, pnp_status;
 };
 
 // ---------------------------------------------------------------- projection
@@ -711,119 +717,6 @@ CAL_HD_NOINLINE inline bool homography_4pt(const double* x, const double* y, con
   H[8] = 1.0;
   (void)nrm;
   return true;
-}
-
-CAL_HD inline uint32_t lcg(uint32_t& s) { s = s * 1664525u + 1013904223u; return s >> 8; }
-
-// findHomography(world_xy, img, RANSAC, thr) on ws.hx/hy/hu/hv (ws.hn points) -> ws.H, ws.inl.
-// Deterministic: all 4-subsets when there are at most NHYP of them, otherwise NHYP LCG samples.
-// Returns (via ws.flag) 1 on success.
-CAL_HD_NOINLINE inline void homography_ransac(const Team& T, Workspace& ws, double thr) {
-  CAL_COUNT(g_ransac);
-  const int n = ws.hn;
-  long long comb = (long long)n * (n - 1) * (n - 2) * (n - 3) / 24;
-  const bool exhaustive = comb <= NHYP;
-  const int nh = exhaustive ? (int)comb : NHYP;
-  const double thr2 = thr * thr;
-  for (int h = T.tid; h < nh; h += T.nt) {
-    int idx[4];
-    if (exhaustive) {
-      // h-th 4-subset in lexicographic order
-      int r = h, a = 0;
-      for (int k = 0; k < 4; ++k) {
-        for (;; ++a) {
-          const int rem = n - a - 1, need = 3 - k;
-          long long c = 1;
-          for (int j = 0; j < need; ++j) c = c * (rem - j) / (j + 1);
-          if (need > rem) c = 0;
-          if (r < c) break;
-          r -= (int)c;
-        }
-        idx[k] = a++;
-      }
-    } else {
-      uint32_t s = 0x9E3779B9u * (uint32_t)(h + 1) + (uint32_t)n;
-      for (int k = 0; k < 4; ++k) {
-        bool dup;
-        do {
-          idx[k] = (int)(lcg(s) % (uint32_t)n);
-          dup = false;
-          for (int j = 0; j < k; ++j) dup |= (idx[j] == idx[k]);
-        } while (dup);
-      }
-    }
-    double x[4], y[4], u[4], v[4], H[9];
-    for (int k = 0; k < 4; ++k) { x[k] = ws.hx[idx[k]]; y[k] = ws.hy[idx[k]]; u[k] = ws.hu[idx[k]]; v[k] = ws.hv[idx[k]]; }
-    int cnt = -1;
-    double esum = 0.0;
-    if (homography_4pt(x, y, u, v, H)) {
-      cnt = 0;
-      for (int i = 0; i < n; ++i) {
-        const double w = H[6] * ws.hx[i] + H[7] * ws.hy[i] + 1.0;
-        const double du = (H[0] * ws.hx[i] + H[1] * ws.hy[i] + H[2]) / w - ws.hu[i];
-        const double dv = (H[3] * ws.hx[i] + H[4] * ws.hy[i] + H[5]) / w - ws.hv[i];
-        const double e = du * du + dv * dv;
-        if (e <= thr2) { ++cnt; esum += e; }
-      }
-    }
-    ws.hyp_cnt[h] = cnt;
-    ws.hyp_err[h] = esum;
-  }
-  T.sync();
-  if (T.tid == 0) {
-    int best = -1;
-    for (int h = 0; h < nh; ++h) {
-      if (ws.hyp_cnt[h] < 4) continue;
-      if (best < 0 || ws.hyp_cnt[h] > ws.hyp_cnt[best] ||
-          (ws.hyp_cnt[h] == ws.hyp_cnt[best] && ws.hyp_err[h] < ws.hyp_err[best])) best = h;
-    }
-    ws.flag = 0;
-    if (best >= 0) {
-      // recompute the winning hypothesis' inlier mask
-      int idx[4];
-      if (exhaustive) {
-        int r = best, a = 0;
-        for (int k = 0; k < 4; ++k) {
-          for (;; ++a) {
-            const int rem = n - a - 1, need = 3 - k;
-            long long c = 1;
-            for (int j = 0; j < need; ++j) c = c * (rem - j) / (j + 1);
-            if (need > rem) c = 0;
-            if (r < c) break;
-            r -= (int)c;
-          }
-          idx[k] = a++;
-        }
-      } else {
-        uint32_t s = 0x9E3779B9u * (uint32_t)(best + 1) + (uint32_t)n;
-        for (int k = 0; k < 4; ++k) {
-          bool dup;
-          do {
-            idx[k] = (int)(lcg(s) % (uint32_t)n);
-            dup = false;
-            for (int j = 0; j < k; ++j) dup |= (idx[j] == idx[k]);
-          } while (dup);
-        }
-      }
-      double x[4], y[4], u[4], v[4], H[9];
-      for (int k = 0; k < 4; ++k) { x[k] = ws.hx[idx[k]]; y[k] = ws.hy[idx[k]]; u[k] = ws.hu[idx[k]]; v[k] = ws.hv[idx[k]]; }
-      homography_4pt(x, y, u, v, H);
-      for (int i = 0; i < n; ++i) {
-        const double w = H[6] * ws.hx[i] + H[7] * ws.hy[i] + 1.0;
-        const double du = (H[0] * ws.hx[i] + H[1] * ws.hy[i] + H[2]) / w - ws.hu[i];
-        const double dv = (H[3] * ws.hx[i] + H[4] * ws.hy[i] + H[5]) / w - ws.hv[i];
-        ws.inl[i] = (du * du + dv * dv <= thr2) ? 1 : 0;
-      }
-      ws.flag = 1;
-    }
-  }
-  T.sync();
-  const bool have = ws.flag != 0;
-  T.sync();
-  bool ok = false;
-  if (have) ok = homography_fit(T, ws, ws.inl, ws.H);     // refit on the consensus set
-  if (T.tid == 0) ws.flag = ok ? 1 : 0;
-  T.sync();
 }
 
 // ---------------------------------------------------------------- pose from a plane homography

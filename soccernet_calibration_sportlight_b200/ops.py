@@ -272,8 +272,11 @@ def line_points(peaks: torch.Tensor, pair_a: torch.Tensor, pair_b: torch.Tensor,
 def pnp(obj: torch.Tensor, img: torch.Tensor, K: torch.Tensor, rvec: torch.Tensor, tvec: torch.Tensor,
         refine: bool) -> bool:
     """Single-camera pose: refine=True is Camera.refine_camera's solvePnPRefineLM (camera.py:105-119,
-    rvec/tvec updated in place), refine=False is Camera.solve_pnp (camera.py:92-103).  All fp64
-    device tensors: obj (n,3), img (n,2), K (3,3), rvec (3), tvec (3)."""
+    rvec/tvec updated in place), refine=False is Camera.solve_pnp (camera.py:92-103: what
+    cv2.solvePnPRansac returns for these matches - P3P on 4, EPnP on 5, seeded RANSAC + refit on
+    more; where OpenCV's RANSAC fails the reference holds uninitialised memory and the least-squares
+    pose is returned instead).  All fp64 device tensors: obj (n,3), img (n,2), K (3,3), rvec (3),
+    tvec (3).  Returns False only when no finite pose exists."""
     n = obj.shape[0]
     ptrs = [_dev(t, torch.float64, "pnp") for t in (obj, img, K, rvec, tvec)]
     with _Launch("pnp", obj.device):
@@ -284,4 +287,4 @@ def pnp(obj: torch.Tensor, img: torch.Tensor, K: torch.Tensor, rvec: torch.Tenso
             ok = torch.zeros(1, dtype=torch.int32, device=obj.device)
             st = _lib.lib().cal_pnp_solve(ptrs[0], ptrs[1], n, ptrs[2], ptrs[3], ptrs[4], ok.data_ptr(), _stream())
     _lib.check(st, "cal_pnp")
-    return True if ok is None else bool(int(ok.item()))
+    return True if ok is None else int(ok.item()) >= 0

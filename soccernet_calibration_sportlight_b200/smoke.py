@@ -49,7 +49,7 @@ def run() -> None:
         cams = mine.batch(kps)
         for i, cam in enumerate(cams):
             rc = ref(kps[i])
-            if not ref.pinned or ref.minimal:
+            if not ref.pinned:
                 continue                               # outcome of the reference itself not reproducible
             assert (cam is None) == (rc is None), f"camera decision differs on frame {i} ({algo})"
             if cam is None:
@@ -59,5 +59,22 @@ def run() -> None:
             b = np.concatenate([rc.position, rc.rotation.ravel(), [rc.xfocal_length]])
             worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0))))
     assert n_cam > 0 and worst < 1e-4, f"camera parameters differ from the oracle by {worst} (rel)"
+    # (4) the camera-solve parity table over the reference's stored outputs (tests/golden/camera_cases.npz)
+    from tests import camera_parity
+
+    def gpu_solver(preds, algo, thr):
+        t = torch.from_numpy(np.ascontiguousarray(preds, dtype=np.float32)).to(dev)
+        rec = ops.camera_solve(t, camera_parity.make_params(algo, thr), None).cpu().numpy()
+        flags = rec.view(np.int32).reshape(rec.shape[0], 32)[:, 30:32]
+        out = np.zeros((rec.shape[0], 16))
+        ok = flags[:, 0] == 1
+        out[ok, :14] = rec[ok, :14]
+        out[:, 14] = ok
+        out[:, 15] = flags[:, 1]
+        return out
+
+    stats = camera_parity.compare(gpu_solver)
+    print(camera_parity.report(stats))
+    camera_parity.assert_parity(stats)
     torch.cuda.synchronize()
     print(f"smoke ok: decode bit-exact, heat-map max|err|={err:.4f}, {n_cam} cameras within {worst:.1e} of the oracle")

@@ -6,6 +6,7 @@
     tests/camera_parity.py against those stored outputs;
   * the Camera / CameraCreator mirrors' host-side members agree with the oracle's."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -51,13 +52,75 @@ def test_oracle_iterative_voter_sample(golden):
 
 
 def test_host_compiled_solver_meets_parity_classes():
+    """Every golden frame whose reference outcome is a function of its inputs is asserted: the
+    exact, minimal (P3P / EPnP shortcut) and ransac (seeded solvePnPRansac) classes."""
     stats = CP.compare(CP.host_solver())
-    ex = stats["exact"]
-    assert ex["n"] > 700
-    assert not ex["failures"], ex["failures"][:5]
-    assert ex["max_err"] < CP.TOL
-    # the other classes are reported by the GPU run (profiles/), not asserted
-    assert set(stats) <= {"exact", "ransac", "minimal", "unpinned", "ill-posed"}
+    print(CP.report(stats))
+    CP.assert_parity(stats)
+    assert set(stats) <= {"exact", "ransac", "minimal", "unpinned", "unconverged", "ill-posed", "per_algorithm"}
+
+
+def _host_lib():
+    CP.host_solver()
+    import ctypes as C
+    return C, C.CDLL(os.path.join(CP.ROOT, "tests", "host_solver", "libhost_solver.so"))
+
+
+def test_restated_solvepnpransac_vs_recorded_opencv_calls():
+    """csrc/solve_pnp_cv.cuh (host build) against every cv2.solvePnPRansac call the reference made on
+    the golden frames (tests/golden/cv_calls.npz): same success flag, same consensus set, same pose."""
+    C, L = _host_lib()
+    z = np.load(os.path.join(CP.ROOT, "tests", "golden", "cv_calls.npz"))
+    vp = C.c_void_p
+    n_ok = n_fail = n_min = 0
+    for j in range(len(z["pnp_n"])):
+        n = int(z["pnp_n"][j])
+        obj, img = np.ascontiguousarray(z["pnp_obj"][j, :n]), np.ascontiguousarray(z["pnp_img"][j, :n])
+        K = np.ascontiguousarray(z["pnp_K"][j])
+        R, t, mask = np.zeros(9), np.zeros(3), C.c_ulonglong(0)
+        st = L.host_pnp_ransac(obj.ctypes.data_as(vp), img.ctypes.data_as(vp), n, K.ctypes.data_as(vp), R.ctypes.data_as(vp),
+                               t.ctypes.data_as(vp), C.byref(mask))
+        tv = z["pnp_tvec"][j]
+        if not z["pnp_ok"][j]:
+            assert st <= 0, j                      # OpenCV's RANSAC fails: so does the restatement
+            n_fail += 1
+            continue
+        if not np.all(np.isfinite(tv)) or np.abs(tv).max() > 1e6 or K[0, 0] == 1.0:
+            continue                               # degenerate inputs (collinear points, K = identity): garbage in both
+        assert st == 1, j
+        Rc = cam_mod.rotation_from_rodrigues(z["pnp_rvec"][j])
+        err = max(np.abs(R.reshape(3, 3) - Rc).max(), np.abs(t - tv).max() / max(1.0, np.abs(tv).max()))
+        mine = {i for i in range(n) if (mask.value >> i) & 1}
+        ref = set(np.nonzero(z["pnp_inliers"][j])[0].tolist()) if n > 5 else set(range(n))
+        if mine != ref:
+            continue                               # (2 of 229: a later sample ties on the inlier count)
+        assert err < 1e-5, (j, n, err)
+        n_ok += 1
+        n_min += n <= 5
+    assert n_ok >= 200 and n_min >= 30 and n_fail >= 200, (n_ok, n_min, n_fail)
+
+
+def test_restated_findhomography_ransac_vs_recorded_opencv_calls():
+    C, L = _host_lib()
+    z = np.load(os.path.join(CP.ROOT, "tests", "golden", "cv_calls.npz"))
+    vp = C.c_void_p
+    good = total = 0
+    for j in range(len(z["hom_n"])):
+        n = int(z["hom_n"][j])
+        if n <= 4 or not z["hom_ok"][j]:
+            continue
+        src, dst = np.ascontiguousarray(z["hom_src"][j, :n]), np.ascontiguousarray(z["hom_dst"][j, :n])
+        H, inl = np.zeros(9), np.zeros(n, np.uint8)
+        ok = L.host_homography_ransac(src.ctypes.data_as(vp), dst.ctypes.data_as(vp), n, C.c_double(float(z["hom_thr"][j])),
+                                      H.ctypes.data_as(vp), inl.ctypes.data_as(vp))
+        Hr = z["hom_H"][j]
+        if np.abs(Hr).max() > 1e6:
+            continue                               # consensus set of collinear points: garbage in both
+        total += 1
+        good += bool(ok) and np.abs(H.reshape(3, 3) - Hr).max() / np.abs(Hr).max() < 1e-6
+    # the misses (4 of 319) are degenerate consensus sets: four collinear points among five (OpenCV returns
+    # a rank-1 matrix), and one whose homography has h33 ~ 0 (both fits equally good, different scale)
+    assert total >= 300 and good >= total - 5, (good, total)
 
 
 def test_host_solver_line_points_merge():
@@ -79,7 +142,7 @@ def test_host_solver_line_points_merge():
         for b in range(24):
             kp = {i: (float(lp[b, i, 0]), float(lp[b, i, 1])) for i in range(57) if not np.isnan(lp[b, i, 0])}
             cam = O.solve(creator, preds[b], kp)
-            if not creator.pinned or creator.minimal or CP.degenerate_goal_view(preds[b], 0.5):
+            if not creator.pinned or CP.degenerate_goal_view(preds[b], 0.5):
                 continue
             ref = O.camera_record(cam)
             assert (got[b, 14] == 1) == (ref[14] == 1), (algo, b)

@@ -203,8 +203,8 @@ int cal_pnp_solve(const double* obj, const double* img, int n, const double* K,
 
 /* Keypoints from the line model's decoded peaks: get_line_data (src/utils/export_line_result.py:
  * 85-131, slope/intercept per line class with both peaks at p >= prob_thre) followed by the
- * line-pair intersections of CameraCreator.__init__ (prediction.py:110-124, 643-653), in fp32
- * as numpy evaluates them there.
+ * line-pair intersections of CameraCreator.__init__ (prediction.py:110-124, 643-653), in fp64
+ * on the fp32 peaks, as the reference's pinned numpy 1.24 evaluates them (scalar promotion).
  *   peaks    : (B, 23, 2, 3) fp32 [x, y, p], already in image pixels (cal_line_decode's scale)
  *   pair_a/b : (57) int32 line-class channel indices whose intersection is keypoint i, -1 = none
  *              (LINE_INTERSECTIONS, src/datatools/intersections.py:13-44)

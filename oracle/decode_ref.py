@@ -141,8 +141,10 @@ def calculate_slope_intercept(p1, p2, delta: float = 0.00001):
 
 
 def get_line_data(heat_loc: np.ndarray, line_cls: Dict[int, str], scale=4, prob_thre: float = 0.2):
-    """export_line_result.py:85-131 (frame 0 of the batch only, as there).  Arithmetic
-    stays in numpy fp32 scalars exactly as the reference's ``x * scale``."""
+    """export_line_result.py:85-131 (frame 0 of the batch only, as there).  The reference pins
+    numpy==1.24.2 (requirements.txt:2), where a float32 scalar times the Python int ``scale``
+    promotes to float64 (legacy scalar promotion; numpy 2 would stay in float32): the coordinates,
+    and with them slope, intercept and the intersections downstream, are float64."""
     heat_loc = np.asarray(heat_loc)
     _, ks, nh, _ = heat_loc.shape
     lines: Dict[str, Tuple[float, float]] = {}
@@ -152,7 +154,7 @@ def get_line_data(heat_loc: np.ndarray, line_cls: Dict[int, str], scale=4, prob_
         for n in range(nh):
             x, y, p = heat_loc[0, k, n]
             if p >= prob_thre:
-                valid.append((x * scale, y * scale, p))
+                valid.append((np.float64(x) * scale, np.float64(y) * scale, p))
         points[line_cls[k]] = valid
         if len(valid) >= 2:
             lines[line_cls[k]] = calculate_slope_intercept(valid[0][:2], valid[1][:2])

@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) pnp_kernel(const double* __rest
   }
 }
 
-// one thread per (frame, keypoint): fp32 arithmetic in the reference's operation order
+// one thread per (frame, keypoint): float64 arithmetic on the float32 peaks, in the reference's
+// operation order (under its pinned numpy 1.24 the float32 scalars promote to float64 at the first
+// ``x * scale``, export_line_result.py:112-121)
 __global__ void line_points_kernel(const float* __restrict__ peaks, int B, int n_lines,
                                    const int32_t* __restrict__ pair_a, const int32_t* __restrict__ pair_b,
                                    float prob_thre, double* __restrict__ out) {
@@ -92,24 +94,25 @@ __global__ void line_points_kernel(const float* __restrict__ peaks, int B, int n
   double ox = CUDART_NAN, oy = CUDART_NAN;
   const int la = pair_a[i], lb = pair_b[i];
   if (la >= 0 && lb >= 0 && la < n_lines && lb < n_lines) {
-    float k[2], c[2];
+    double k[2], c[2];
     bool ok = true;
     for (int q = 0; q < 2; ++q) {
       const float* p = peaks + (static_cast<size_t>(b) * n_lines + (q == 0 ? la : lb)) * 6;
       // get_line_data: both peaks must pass the threshold (export_line_result.py:112-126)
       if (!(p[2] >= prob_thre) || !(p[5] >= prob_thre)) { ok = false; break; }
-      // calculate_slope_intercept (:51-82): identical points -> no line
+      // calculate_slope_intercept (:51-82): identical points -> (None, None); the reference's
+      // CameraCreator.__init__ would then raise on that line pair - here the pair yields no keypoint
       if (p[0] == p[3] && p[1] == p[4]) { ok = false; break; }
-      const float slope = __fdiv_rn(__fsub_rn(p[4], p[1]), __fadd_rn(__fsub_rn(p[3], p[0]), 0.00001f));
+      const double x1 = p[0], y1 = p[1], x2 = p[3], y2 = p[4];
+      const double slope = (y2 - y1) / (x2 - x1 + 0.00001);
       k[q] = slope;
-      c[q] = __fsub_rn(p[1], __fmul_rn(slope, p[0]));
+      c[q] = y1 - slope * x1;
     }
     // line_eq_intersection (prediction.py:643-653)
-    if (ok && fabsf(__fsub_rn(k[0], k[1])) > 1e-4f) {
-      const float x = __fdiv_rn(__fsub_rn(c[1], c[0]), __fsub_rn(k[0], k[1]));
-      const float y = __fadd_rn(__fmul_rn(k[0], x), c[0]);
-      ox = static_cast<double>(x);
-      oy = static_cast<double>(y);
+    if (ok && fabs(k[0] - k[1]) > 1e-4) {
+      const double x = (c[1] - c[0]) / (k[0] - k[1]);
+      ox = x;
+      oy = k[0] * x + c[0];
     }
   }
   out[2 * idx] = ox;

@@ -4,6 +4,7 @@
 // decisions are taken on values in the shared workspace after a sync, so all threads follow
 // the same path.
 #pragma once
+#include <string.h>
 #include "solve_core.cuh"
 #include "solve_pnp_cv.cuh"
 
@@ -532,16 +533,23 @@ CAL_HD_NOINLINE inline bool k_from_homography(const double* H, double ppx, doubl
   return isfinite(*fx) && isfinite(*fy);
 }
 
+// memo key of a point selection: ids AND coordinates (a line-intersection point merged at one
+// threshold can be replaced by the detected keypoint of the same id at the next)
 CAL_HD inline unsigned long long points_mask(const Points& pts) {
-  unsigned long long m = 0;
-  for (int k = 0; k < pts.n; ++k) m |= 1ull << pts.id[k];
-  return m;
+  unsigned long long h = 1469598103934665603ull;
+  for (int k = 0; k < pts.n; ++k) {
+    unsigned long long w[3];
+    w[0] = (unsigned long long)pts.id[k];
+    memcpy(&w[1], &pts.x[k], 8);
+    memcpy(&w[2], &pts.y[k], 8);
+    for (int j = 0; j < 3; ++j) { h ^= w[j]; h *= 1099511628211ull; }
+  }
+  return h ^ ((unsigned long long)pts.n << 58);
 }
 
 // get_camera_from_homography: ws.hom / ws.hom_rmse; hom.ok = 0 when the reference returns None
 CAL_HD_NOINLINE inline void homography_camera(const Team& T, Workspace& ws, const CalSolveParams& P, const Points& pts) {
-  // same point set as the last call (line points never change a detected id's coordinates
-  // within a frame): the result is still in ws.hom
+  // same point set (ids and coordinates) as the last call: the result is still in ws.hom
   const unsigned long long mask = points_mask(pts);
   const bool memo = ws.hom_memo_valid && ws.hom_mask == mask;
   T.sync();

@@ -21,7 +21,12 @@ from .hrnet import w48_config
 class CalibrationPipeline:
     """workload 'kp_decode': keypoint net + decode only (BASELINE config 2);
     'keypoints': keypoint net + decode + camera solve (what make_submit.py runs,
-    LINES_FILE=None); 'full': + line net + two-peak decode feeding line intersections."""
+    LINES_FILE=None); 'full': + line net + two-peak decode feeding line intersections.
+
+    ``size`` = (H, W) of the image the keypoints, line peaks and cameras are expressed in (the
+    reference's prediction-transform ``size`` and CameraCreator ``img_size``, 540 x 960 everywhere in
+    its configs); the network input may have any resolution of the same aspect ratio (BASELINE
+    config 5): both decoders rescale to ``size``."""
 
     def __init__(self, device="cuda:0", workload: str = "keypoints", size=(540, 960),
                  kp_state_dict=None, line_state_dict=None, camera_kwargs: Optional[dict] = None,
@@ -51,6 +56,7 @@ class CalibrationPipeline:
             from .prediction import CameraCreator, MAKE_SUBMIT_KWARGS
             from .pitch import PITCH_POINTS
             kw = dict(MAKE_SUBMIT_KWARGS if camera_kwargs is None else camera_kwargs)
+            kw.setdefault("img_size", (self.size[1], self.size[0]))       # (W, H), prediction.py:44
             self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
 
     @torch.no_grad()
@@ -62,6 +68,12 @@ class CalibrationPipeline:
         keypoints (benchmarks with random-init weights, whose confidences never pass a threshold)."""
         x = frames.to(self.device, non_blocking=True)
         line_pts = None
+        if self.line_model is not None:
+            # line heat maps are a quarter of the network input: peaks -> `size` coordinates
+            sy, sx = self.size[0] / x.shape[-2], self.size[1] / x.shape[-1]
+            if abs(sx - sy) > 1e-3 * sx:
+                raise ValueError(f"network input {tuple(x.shape[-2:])} and size {self.size} differ in aspect ratio")
+            self.line_model.prediction_transform.scale = 4.0 * sx
         if self.line_model is not None and self.two_streams:
             # the two networks are independent: on two streams the ramp-up / tail of every
             # (persistent, one CTA per SM) kernel of one network is filled by the other's

@@ -55,7 +55,8 @@ def calculate_slope_intercept(p1, p2, delta: float = 0.00001):
 
 def get_line_data(heat_loc, scale=4, prob_thre: float = 0.2, frame: int = 0):
     """export_line_result.py:85-131 for one frame of the decoded (B,23,2,3) peaks:
-    -> (lines {class: (slope, intercept)}, points {class: [(x, y, p), ...]})."""
+    -> (lines {class: (slope, intercept)}, points {class: [(x, y, p), ...]}).  Coordinates, slopes and
+    intercepts are float64, as under the reference's pinned numpy 1.24 (float32 scalar x Python int)."""
     if isinstance(heat_loc, torch.Tensor):
         heat_loc = heat_loc.detach().cpu().numpy()
     heat_loc = np.asarray(heat_loc)
@@ -66,7 +67,7 @@ def get_line_data(heat_loc, scale=4, prob_thre: float = 0.2, frame: int = 0):
         for n in range(heat_loc.shape[2]):
             x, y, p = heat_loc[frame, k, n]
             if p >= prob_thre:
-                valid.append((x * scale, y * scale, p))
+                valid.append((np.float64(x) * scale, np.float64(y) * scale, p))
         points[LINE_CLS[k]] = valid
         if len(valid) >= 2:
             lines[LINE_CLS[k]] = calculate_slope_intercept(valid[0][:2], valid[1][:2])

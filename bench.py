@@ -169,7 +169,9 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOADS[args.workload][0], "name": args.workload, "frames_per_step": 1},
+        "config": {"workload": WORKLOADS[args.workload][0], "name": args.workload, "frames_per_step": 1,
+                   "note": "one CPU process on rank 0's host cores whatever --gpus is: the ratio to an N-GPU line "
+                           "compares N GPUs with one host"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
@@ -214,9 +216,15 @@ def run_b200(args, rank, world, local_rank):
     from soccernet_calibration_sportlight_b200 import sharding
 
     def step(x):
-        out = pipe(x, keypoints_override=synth) if solve else pipe(x)
+        # the solve of this batch is enqueued on the pipeline's solve stream and runs under the next
+        # batch's networks (pipeline.overlap_solve); the timed region ends with a device-wide synchronize
+        out = pipe(x, keypoints_override=synth, defer_solve=True) if solve else pipe(x)
         res = result_of(out)
         if world > 1:                             # the one collective of the path: gather the records
+            st = out.get("solve_stream")
+            if st is not None:
+                with torch.cuda.stream(st):
+                    return sharding.all_gather_records(res, world * B)
             return sharding.all_gather_records(res, world * B)
         return res
 
@@ -281,6 +289,31 @@ def run_b200(args, rank, world, local_rank):
     h2d = host.numel() * host.element_size()
     d2h = res_host.numel() * res_host.element_size()
 
+    # N > 1, outside every timed region: the gathered keypoints and camera records must equal, bit for bit,
+    # what rank 0 computes ALONE for the same frames (every rank's inputs are regenerated from their seeds)
+    mg_check = None
+    if world > 1:
+        out = pipe(frames, keypoints_override=synth) if solve else pipe(frames)
+        mine = [out["keypoints"].contiguous()] + ([out["cameras"].contiguous()] if solve else [])
+        gathered = []
+        for t in mine:
+            g_all = torch.empty((world * B,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+            dist.all_gather_into_tensor(g_all, t)
+            gathered.append(g_all)
+        if rank == 0:
+            same = [True] * len(mine)
+            for r in range(world):
+                gr = torch.Generator().manual_seed(1234 + r)
+                fr = torch.randint(0, 256, (B, 3, nh, nw), generator=gr, dtype=torch.uint8).float().div_(255.0).to(dev)
+                sy = torch.from_numpy(synthetic_keypoints(B, seed=100 + r)).to(dev) if solve else None
+                o = pipe(fr, keypoints_override=sy) if solve else pipe(fr)
+                alone = [o["keypoints"]] + ([o["cameras"]] if solve else [])
+                for k, (a, g_all) in enumerate(zip(alone, gathered)):
+                    same[k] = same[k] and bool(torch.equal(a.contiguous().view(torch.uint8), g_all[r * B:(r + 1) * B].view(torch.uint8)))
+            mg_check = {"ranks": world, "what": "NCCL-gathered results of all ranks vs rank 0 computing every rank's frames alone",
+                        "keypoints_bit_identical": same[0], "records_bit_identical": same[1] if solve else None}
+        barrier()
+
     # per-kernel device time: one extra step with CUDA events around every launch, the two networks
     # on ONE stream so that a launch's event pair times that launch alone (in the timed region the
     # networks run on two streams and their kernels overlap)
@@ -339,14 +372,24 @@ def run_b200(args, rank, world, local_rank):
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (tcgen05); f32 decode; f64 camera solve",
         "data": "synthetic",
-        "config": {"workload": desc, "name": args.workload, "batch_per_gpu": B, "global_batch": world * B,
+        "config": {"workload": desc if (nh, nw) == (H_IMG, W_IMG) else
+                   desc.replace("960x540", f"{nw}x{nh} network input, keypoints in 960x540 coordinates").replace(
+                       "BASELINE config 2", "BASELINE config 5 sweep").replace("BASELINE config 3", "BASELINE config 5 sweep"),
+                   "name": args.workload, "batch_per_gpu": B, "global_batch": world * B,
                    "resolution": [nw, nh], "weights": "random-init HRNet-w48 (seeded)",
+                   "camera_solve_inputs": ("synthetic keypoints of plausible cameras (keypoints_override): random-init weights "
+                                           "give conf ~ 1/58 < every threshold; the networks' own decoded keypoints are still "
+                                           "produced every step") if solve else None,
                    "l2": "inputs larger than L2 (398 MB of frames + GBs of activations per step)",
+                   "camera_solve_schedule": (("second stream, under the next batch's networks (co-resident blocks, "
+                                              f"{pipe.solve_headroom} B shared-memory headroom)") if pipe.overlap_solve
+                                             else "same stream, after the networks") if solve else None,
                    "parallelism": f"frame shards x{world}, one NCCL all-gather of the results" if world > 1 else "single GPU"},
         "e2e": {"value": frames_total / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                 "h2d_copy_ms_alone": h2d_ms, "h2d_gbps_alone": host.numel() * host.element_size() / h2d_ms / 1e6},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "decode": dec, "kernels_ms_per_step": kernels_ms,
+        "multi_gpu_check": mg_check,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)

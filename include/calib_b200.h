@@ -41,6 +41,13 @@ typedef enum CalStatus {
 int cal_abi_version(void);
 const char* cal_last_error(void);
 
+/* Shared memory (bytes per SM, 0..98304) the persistent tcgen05 kernels leave unused so that blocks of
+ * cal_camera_solve (one frame each: ~39 KB, 64 threads x <= 168 registers) can be co-resident with
+ * them: the reference solves the cameras of a batch in a 16-process CPU pool while the GPU already
+ * runs the next batch (src/utils/make_submit.py:53-73); here the solve of batch i runs UNDER the
+ * networks of batch i+1 on a second stream.  Default 0, or the environment variable CAL_SMEM_HEADROOM. */
+int cal_set_smem_headroom(int bytes);
+
 /* ------------------------------------------------------------------ decode -- */
 
 /* Keypoint heat-map decode.

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcalib_b200.so")
 CAL_MAX_SOURCES = 6
 
 EXPORTS = [
-    "cal_abi_version", "cal_last_error", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
+    "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points",
     "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",

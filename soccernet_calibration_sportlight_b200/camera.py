@@ -131,15 +131,65 @@ class Camera:
         self.tangential_disto = np.array(d["tangential_distortion"], dtype="float")
         self.thin_prism_disto = np.array(d["thin_prism_distortion"], dtype="float")
 
+    def distort(self, point):
+        """camera.py:220-247: rational radial (k1..k3 over k4..k6), tangential and thin-prism terms on a
+        point of the normalised image plane; the result is float32 as there.  With the all-zero
+        coefficients of this path it only rounds the point to float32."""
+        x, y = point[0], point[1]
+        r2 = x * x + y * y
+        radius = np.sqrt(r2)
+        num = den = 1
+        for i in range(3):
+            num += self.radial_distortion[i] * radius ** (2 * (i + 1))
+            den += self.radial_distortion[i + 3] * radius ** (2 * (i + 1))
+        f = num / den
+        t, q = self.tangential_disto, self.thin_prism_disto
+        xd = x * f + 2 * t[0] * x * y + t[1] * (radius ** 2 + 2 * x ** 2) + q[0] * radius ** 2 + q[1] * radius ** 4
+        yd = y * f + 2 * t[1] * x * y + t[0] * (radius ** 2 + 2 * y ** 2) + q[2] * radius ** 2 + q[3] * radius ** 4
+        return np.array([xd, yd], dtype=np.float32)
+
+    def estimate_calibration_matrix_from_plane_homography(self, homography):
+        """camera.py:366-426 (Hartley & Zisserman, algorithm 8.2): the image of the absolute conic w from
+        the two circular-point constraints of a plane homography plus zero skew, square pixels and the
+        principal-point ratio; K = (chol(w)^T)^-1 normalised.  Only the focal lengths are kept, the
+        principal point stays at the image centre.  Returns (ok, K) like the reference; on a
+        non-positive-definite w nothing is changed and (False, identity) comes back.
+        (csrc/solve_cascade.cuh k_from_homography is the same computation inside the batched solve.)"""
+        h = np.reshape(np.asarray(homography, dtype=np.float64), 9)
+        c1, c2 = h[[0, 3, 6]], h[[1, 4, 7]]                   # first two columns of H
+
+        def quad(a, b):                                       # a^T w b in the unknowns (w11 w12 w22 w13 w23 w33)
+            return [a[0] * b[0], a[0] * b[1] + a[1] * b[0], a[1] * b[1], a[0] * b[2] + a[2] * b[0],
+                    a[1] * b[2] + a[2] * b[1], a[2] * b[2]]
+        A = np.zeros((5, 6))
+        A[0, 1] = 1.0                                         # zero skew
+        A[1, 0], A[1, 2] = 1.0, -1.0                          # square pixels
+        A[2, 3], A[2, 4] = self.principal_point[1] / self.principal_point[0], -1.0
+        A[3] = quad(c1, c2)                                   # h1^T w h2 = 0
+        A[4] = np.subtract(quad(c1, c1), quad(c2, c2))        # h1^T w h1 = h2^T w h2
+        w = np.linalg.svd(A)[2][-1]
+        W = np.array([[w[0], w[1], w[3]], [w[1], w[2], w[4]], [w[3], w[4], w[5]]]) / w[5]
+        try:
+            L = np.linalg.cholesky(W)
+        except np.linalg.LinAlgError:
+            return False, np.eye(3)
+        K = np.linalg.inv(L.T)
+        K /= K[2, 2]
+        self.xfocal_length, self.yfocal_length = K[0, 0], K[1, 1]
+        self.principal_point = (self.image_width / 2, self.image_height / 2)
+        self.calibration = np.array([[self.xfocal_length, 0, self.principal_point[0]],
+                                     [0, self.yfocal_length, self.principal_point[1]],
+                                     [0, 0, 1]], dtype="float")
+        return True, K
+
     def project_point(self, point3D, distort=True):
-        """camera.py:249-268 (zero distortion on this path: distort() only rounds the normalised
-        point to float32, camera.py:247)."""
+        """camera.py:249-268."""
         p = self.rotation @ np.transpose(np.asarray(point3D) - self.position)
         if p[2] <= 1e-3:
             return np.zeros(3)
         p = p / p[2]
         if distort:
-            p = np.array([p[0], p[1]], dtype=np.float32)
+            p = self.distort(p)
         return np.array([p[0] * self.xfocal_length + self.principal_point[0],
                          p[1] * self.yfocal_length + self.principal_point[1], 1])
 

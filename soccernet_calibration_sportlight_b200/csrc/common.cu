@@ -35,6 +35,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Shared memory the persistent tcgen05 kernels leave free on every SM so that a camera_solve_kernel
+// block (one frame, ~39 KB + 64 threads x 168 registers) can be co-resident with them: the solve of
+// batch i then runs UNDER the networks of batch i+1 instead of after them (pipeline.py).
+// CAL_SMEM_HEADROOM (bytes) or cal_set_smem_headroom(); 0 = the kernels take all they can use.
+static int g_smem_headroom = [] { const char* e = getenv("CAL_SMEM_HEADROOM"); return e ? atoi(e) : 0; }();
+int smem_headroom() { return g_smem_headroom; }
+
 bool pdl_enabled() {
   // opt-in: measured on B200 at 1.5-3 % per back-to-back 3x3 launch (80 -> 78 us), within run-to-run noise
   static const bool on = [] { const char* e = getenv("CAL_PDL"); return e && e[0] == '1'; }();
@@ -72,4 +79,9 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 }  // namespace cal
 
 extern "C" int cal_abi_version(void) { return CAL_ABI_VERSION; }
+extern "C" int cal_set_smem_headroom(int bytes) {
+  CAL_REQUIRE(bytes >= 0 && bytes <= 96 * 1024, CAL_E_INVALID, "cal_set_smem_headroom: %d bytes (0..98304)", bytes);
+  cal::g_smem_headroom = bytes;
+  return CAL_OK;
+}
 extern "C" const char* cal_last_error(void) { return cal::g_err; }

@@ -41,6 +41,8 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 int launch_conv3x3_halo(const CalConvArgs* a, void* stream);
 // Programmatic dependent launch between the path's own kernels (opt-in: CAL_PDL=1).
 bool pdl_enabled();
+// bytes of shared memory per SM the persistent kernels leave to a co-resident camera-solve block
+int smem_headroom();
 
 // ----------------------------------------------------------------------------- device
 #ifdef __CUDACC__

@@ -17,6 +17,14 @@
 //     pair and the tensor pipe queues only a couple of MMAs (tools/gpu_mma_rate.py), so the issue
 //     loop is a handful of instructions per MMA, a stage's wait comes before the previous
 //     stage's commit, and work items of T = 2 tiles share every slice where TMEM allows;
+//   * C <= 64 (the 135x240 branch: a quarter of the step): an MMA of M = 128, K = 16 reads its A operand
+//     from shared memory in 32 cycles whatever N is, so N = 48 runs at 24 / 44 of the tensor rate.  The
+//     three taps of one filter ROW share the A view when the column shift is taken out of the
+//     operand: G_dx[q] = sum_dy W[dy,dx] X[q + dy*TWp] for dx = 0..2 is ONE accumulation with
+//     N = 3 * Cout (the resident weight slices of a filter row are contiguous in shared memory), three
+//     MMAs per K step instead of nine, math-bound (72 cycles at N = 144).  out[p] = G_0[p] + G_1[p+1]
+//     + G_2[p+2] is formed by the epilogue: with TWp <= 32 a patch row lies inside one warp's 32 TMEM
+//     lanes, so the two shifts are warp shuffles (template DX);
 //   * epilogue: TMEM -> registers (32 columns per tcgen05.ld) -> bias / residual / ReLU -> fp16
 //     -> 32-byte-sector stores straight from registers (st.global.v8). A swizzled staging tile
 //     drained by TMA stores remains as a build option (-DCAL_HALO_STAGED): its shared-memory traffic
@@ -60,6 +68,7 @@ struct HaloParams {
   int w_slices;            // weights are slice-major: slice s = rows [s*Cout_rows, (s+1)*Cout_rows) of a (.., 64) matrix
   int cout_rows;
   int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
+  int dx;               // filter-row grouping: N = 3 * mma_n per MMA, column shifts in the epilogue (template DX)
   int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
   int w_resident, b_stages, b_slice_bytes;
@@ -114,7 +123,7 @@ __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool RESIDENT, int T>
+template <bool RESIDENT, int T, bool DX = false>
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmBp, const __grid_constant__ CUtensorMap tmY,
@@ -237,7 +246,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // word, the tap order and the tiles per item are compile-time constants.
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
-    const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+    const uint32_t idesc = make_idesc_f16(128, DX ? 3 * p.mma_n : p.mma_n);
     const uint64_t desc0 = make_smem_desc(0, 128, 2);      // everything but the start address
     const uint32_t dhi = static_cast<uint32_t>(desc0 >> 32), dlo = static_cast<uint32_t>(desc0);
     uint32_t tap_off[9];
@@ -280,6 +289,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (stamp) H_STAMP(1, mi, 2);
         const int nk = (cc == ncc - 1) ? ksteps_last : 4;       // pad lanes of the last chunk are zero: skip them
         const uint32_t w_cc = w_lo0 + cc * w_step;
+        if (DX) {
+          // one MMA per (filter row, K step): A = the patch shifted by dy rows of TWp pixels,
+          // B = the three taps of that filter row (3 * mma_n weight rows, contiguous resident slices)
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            if (do_mma) {
+              const uint32_t at = a_lo + tap_off[dy * 3];
+              const uint32_t bl = w_cc + dy * 3 * w_tap;
+              const uint32_t first = (cc | dy) != 0;
+              umma_f16_lo(d_tmem, at, bl, dhi, idesc, first);
+              if (nk > 1) umma_f16_lo(d_tmem, at + 2, bl + 2, dhi, idesc, 1);
+              if (nk > 2) umma_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc, 1);
+              if (nk > 3) umma_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc, 1);
+            }
+            if (dy == 1 && cc == ncc - 1 && has_next) {
+              const int as_n = (as + 1 == n_acc) ? 0 : as + 1;
+              const uint32_t aph_n = (as_n == 0) ? (aphase ^ 1) : aphase;
+              mbar_wait(&tempty[as_n], aph_n ^ 1);
+              const int sa_n = (sa + 1 == a_stages) ? 0 : sa + 1;
+              const uint32_t pha_n = (sa_n == 0) ? (pha ^ 1) : pha;
+              mbar_wait(&fullA[sa_n], pha_n);
+              tc_fence_after();
+              pre_next = true;
+            }
+          }
+        } else {
 #pragma unroll
         for (int t9 = 0; t9 < 9; ++t9) {
           if (!RESIDENT && g == 0 && !b_ready) mbar_wait(&fullB[sb], phb);
@@ -330,6 +365,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             pre_next = true;
           }
         }
+        }
         if (issuer) umma_commit(&emptyA[sa]);
         __syncwarp();
         a_lo += a_step;
@@ -355,7 +391,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ms = r * p.TW + xx;                            // row of this pixel in the dense R x TW staging tile
     const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
     uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
-    const bool prefetch_res = (p.res != nullptr) && groups_total <= 2 && T <= 2;
+    const bool prefetch_res = !DX && (p.res != nullptr) && groups_total <= 2 && T <= 2;
     // residual rows are fetched one of this group's tiles ahead (the accumulator ring lets the
     // MMAs run far ahead, so nothing else would hide the read latency)
     uint4 rnext[8];
@@ -403,6 +439,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool valid = (xx < p.TW) && (y < p.H) && (x < p.W);
       const size_t pix = (static_cast<size_t>(tc.b) * p.H + y) * p.W + x;
       const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
+      uint4 rdx[8];                                          // DX: this pixel's residual channels, in flight while the accumulator completes
+      if (DX) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rdx[q] = make_uint4(0, 0, 0, 0);
+        if (rrow) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 8 < p.mma_n) rdx[q] = ldg_nc_v4(rrow + q * 8);
+        }
+      }
       uint4 rpre[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) rpre[q] = rnext[q];
@@ -477,7 +523,43 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       };
-      {
+      if (DX) {
+        // out[p] = G_0[p] + G_1[p + 1] + G_2[p + 2]: the three column groups of the accumulator, the
+        // shifts by warp shuffles (a patch row of TWp <= 32 pixels lies inside this warp's lanes; lanes
+        // whose neighbours belong to the next row are the two halo columns, which are not stored)
+        // 16-channel blocks of the output pixel (Cout_pad = 64: four)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          uint32_t o[8];
+          if (cb * 16 < p.mma_n) {
+            uint32_t g0[16], g1[16], g2[16];
+            tmem_ld16(taddr + cb * 16, g0);
+            tmem_ld16(taddr + p.mma_n + cb * 16, g1);
+            tmem_ld16(taddr + 2 * p.mma_n + cb * 16, g2);
+            tmem_ld_wait();
+            const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const float* bb = s_bias + tc.n0 + cb * 16;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = __uint_as_float(g0[2 * j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j]), 1) +
+                        __shfl_down_sync(0xffffffffu, __uint_as_float(g2[2 * j]), 2);
+              float b = __uint_as_float(g0[2 * j + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j + 1]), 1) +
+                        __shfl_down_sync(0xffffffffu, __uint_as_float(g2[2 * j + 1]), 2);
+              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+              a += bb[2 * j] + __low2float(rh);
+              b += bb[2 * j + 1] + __high2float(rh);
+              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+              o[j] = h_pack_half2(a, b);
+            }
+          } else {
+            // pad channels stay zero
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = 0u;
+          }
+          if (valid && !(p.ablate & 2)) stg_v8(yrow + cb * 16, o);
+        }
+      } else {
         for (int g = 0; g < groups_total; ++g) {
           uint4 rq[4];
           if (prefetch_res) {
@@ -548,8 +630,12 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   p.B = a->B; p.H = a->Hout; p.W = a->Wout; p.Cout_pad = a->Cout_pad;
   // tile geometry: few tiles (MMA rows are spent on every tile, used or not) and a small halo
   // patch (L2 -> SM bytes per tile)
+  // filter-row grouping (template DX) applies to the single-chunk, single-N-tile layers whose three taps of a
+  // filter row fit one MMA: C <= 64 in, Cout_rows <= 80 out; it needs a patch row inside one warp (TWp <= 32)
+  static const bool dx_enabled = [] { const char* e = getenv("CAL_CONV_DX"); return !(e && e[0] == '0'); }();
+  const bool dx_shape = dx_enabled && a->Cin_pad == 64 && a->Cout_pad == 64 && a->Cout_rows % 8 == 0 && 3 * a->Cout_rows <= 256;
   long best = -1;
-  for (int twp = 16; twp <= 128; twp *= 2) {
+  for (int twp = 16; twp <= (dx_shape ? 32 : 128); twp *= 2) {
     const int tw = twp - 2, r = 128 / twp;
     const long tiles = static_cast<long>((a->Wout + tw - 1) / tw) * ((a->Hout + r - 1) / r);
     const long cost = tiles * (128 * 4 + (r + 2) * twp);
@@ -598,8 +684,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   // groups of a T = 2 item read their residual rows at the same moment: T = 1 there (178 vs 193 us).
   const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + H_MAX_BIAS * 4;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
-  const int budget_res = 224 * 1024 - 1024 - tail - (H_STAGED_BUILD ? 2 * p.nblk * H_STAGE_BLOCK : 0);   // (evaluated before any N split)
-  const int budget_ring = 224 * 1024 - 1024 - tail;
+  const int avail = 224 * 1024 - smem_headroom();
+  const int budget_res = avail - 1024 - tail - (H_STAGED_BUILD ? 2 * p.nblk * H_STAGE_BLOCK : 0);   // (evaluated before any N split)
+  const int budget_ring = avail - 1024 - tail;
   auto set_tiles = [&](int T) {
     p.T = T;
     p.RI = p.R * T;
@@ -617,6 +704,12 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   set_tiles((max_tiles >= 2 && fits2 && (force_tiles || !a->res)) ? 2 : 1);
   if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget_res) {
     p.w_resident = 1;
+    if (dx_shape && p.b_slice_bytes == p.mma_n * 128) {
+      // (slices of mma_n * 128 bytes are contiguous: a filter row's three taps form one 3 * mma_n-row operand)
+      p.dx = 1;
+      p.acc_stride = (3 * p.mma_n + 31) & ~31;
+      set_tiles(1);
+    }
     // Outputs go straight from registers to global memory (two full 32-byte sectors per lane and
     // 32-channel group). The alternative - a swizzled staging tile drained by TMA stores,
     // CAL_CONV_DIRECT=0 in a -DCAL_HALO_STAGED build - costs 32 KB of shared-memory traffic per tile next to the MMA operand
@@ -683,6 +776,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -737,9 +831,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     static const bool show = getenv("CAL_DEBUG_CONFIG") != nullptr;
     if (show)
       fprintf(stderr, "halo conv %dx%d Cin_pad %d Cout_pad %d: N_tile %d G %d TWp %d R %d T %d resident %d a_stages %d b_stages %d "
-                      "slice %d B n_acc %d cluster %d smem %zu grid %d items %d\n",
+                      "slice %d B n_acc %d cluster %d smem %zu grid %d items %d dx %d\n",
               a->Hout, a->Wout, a->Cin_pad, a->Cout_pad, p.N_tile, p.G, p.TWp, p.R, p.T, p.w_resident, p.a_stages, p.b_stages,
-              p.b_slice_bytes, p.n_acc, p.cluster, smem, grid, p.total_tiles);
+              p.b_slice_bytes, p.n_acc, p.cluster, smem, grid, p.total_tiles, p.dx);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -755,7 +849,8 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  if (p.w_resident && p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 2>, tmA, tmB, tmBp, tmY, p));
+  if (p.w_resident && p.dx) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1, true>, tmA, tmB, tmBp, tmY, p));
+  else if (p.w_resident && p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 2>, tmA, tmB, tmBp, tmY, p));
   else if (p.w_resident) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1>, tmA, tmB, tmBp, tmY, p));
   else if (p.T == 4) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 4>, tmA, tmB, tmBp, tmY, p));
   else if (p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 2>, tmA, tmB, tmBp, tmY, p));

@@ -590,7 +590,8 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
   p.n_acc = TMEM_COLS / p.acc_stride;
   if (p.n_acc > MAX_ACC) p.n_acc = MAX_ACC;
   const int tail_bytes = (2 * MAX_STAGES + 2 * MAX_ACC) * 8 + 16 + MAX_BIAS * 4;
-  int stages = (200 * 1024 - tail_bytes) / stage_bytes;
+  const int avail = 224 * 1024 - smem_headroom() < 200 * 1024 ? 224 * 1024 - smem_headroom() : 200 * 1024;
+  int stages = (avail - 1024 - tail_bytes) / stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   CAL_REQUIRE(stages >= 2, CAL_E_UNSUPPORTED, "cal_conv2d: tile does not fit shared memory");
   p.stages = stages;

@@ -12,8 +12,12 @@ namespace cal {
 namespace {
 
 constexpr int SOLVE_THREADS = 64;    // two warps: the solver is a chain of short team-parallel loops, barrier latency dominates
+// Register budget: 6 blocks per SM = at most 168 registers per thread, so that a solve block fits next to
+// a persistent 320-thread x 168-register conv CTA (53,760 + 10,752 of the SM's 65,536 registers) and the
+// solve of one batch can run under the networks of the next (common.cu: smem_headroom).
+constexpr int SOLVE_MIN_BLOCKS = 6;
 
-__global__ void __launch_bounds__(SOLVE_THREADS) camera_solve_kernel(const float* __restrict__ preds,
+__global__ void __launch_bounds__(SOLVE_THREADS, SOLVE_MIN_BLOCKS) camera_solve_kernel(const float* __restrict__ preds,
                                                                      const double* __restrict__ line_pts,
                                                                      const __grid_constant__ CalSolveParams P,
                                                                      CalCameraRecord* __restrict__ out) {

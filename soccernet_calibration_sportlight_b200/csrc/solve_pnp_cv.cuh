@@ -44,13 +44,16 @@ struct CvRng {
 // values in decreasing order, Vt (n x n, may be null) the right singular vectors as rows.  Rows of
 // zero singular values (i < n1) are filled with the +-1/m pseudo-random pattern, orthogonalised
 // against the rows before them - only when the singular vectors are asked for (Vt != null).
-CAL_HD_NOINLINE inline void jacobi_svd(double* At, int astep, double* W, double* Vt, int vstep, int m, int n, int n1) {
+// want_v = false: the caller needs U only; Vt is then any non-null pointer and is left untouched
+// (the rotations of V have no influence on U or W).
+CAL_HD_NOINLINE inline void jacobi_svd(double* At, int astep, double* W, double* Vt, int vstep, int m, int n, int n1,
+                                       bool want_v = true) {
   const double eps = DBL_EPSILON * 10, minval = DBL_MIN;
   for (int i = 0; i < n; ++i) {
     double sd = 0;
     for (int k = 0; k < m; ++k) { const double t = At[i * astep + k]; sd += t * t; }
     W[i] = sd;
-    if (Vt) {
+    if (Vt && want_v) {
       for (int k = 0; k < n; ++k) Vt[i * vstep + k] = 0;
       Vt[i * vstep + i] = 1;
     }
@@ -85,7 +88,7 @@ CAL_HD_NOINLINE inline void jacobi_svd(double* At, int astep, double* W, double*
         }
         W[i] = a; W[j] = b;
         changed = true;
-        if (Vt) {
+        if (Vt && want_v) {
           double* Vi = Vt + i * vstep;
           double* Vj = Vt + j * vstep;
           for (int k = 0; k < n; ++k) {
@@ -110,7 +113,8 @@ CAL_HD_NOINLINE inline void jacobi_svd(double* At, int astep, double* W, double*
       { const double t = W[i]; W[i] = W[j]; W[j] = t; }
       if (Vt) {
         for (int k = 0; k < m; ++k) { const double t = At[i * astep + k]; At[i * astep + k] = At[j * astep + k]; At[j * astep + k] = t; }
-        for (int k = 0; k < n; ++k) { const double t = Vt[i * vstep + k]; Vt[i * vstep + k] = Vt[j * vstep + k]; Vt[j * vstep + k] = t; }
+        if (want_v)
+          for (int k = 0; k < n; ++k) { const double t = Vt[i * vstep + k]; Vt[i * vstep + k] = Vt[j * vstep + k]; Vt[j * vstep + k] = t; }
       }
     }
   }
@@ -361,8 +365,8 @@ struct Epnp5 {
         ut[i * 12 + j] = s; ut[j * 12 + i] = s;
       }
     {
-      double D[12], Vt[144];
-      jacobi_svd(ut, 12, D, Vt, 12, 12, 12, 12);
+      double D[12];
+      jacobi_svd(ut, 12, D, D /* unused */, 12, 12, 12, 12, false);
     }
     double L[60], rho[6];
     {

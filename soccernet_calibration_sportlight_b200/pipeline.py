@@ -35,7 +35,16 @@ class CalibrationPipeline:
             raise ValueError(workload)
         self.device = torch.device(device)
         self.two_streams = os.environ.get("CAL_TWO_STREAMS", "1") != "0"
+        # the camera solve of batch i under the networks of batch i+1 (the reference overlaps them too:
+        # a 16-process CPU pool solves while the GPU runs on, make_submit.py:53-73).  The solve kernel is
+        # 64 small blocks; the persistent conv kernels leave `solve_headroom` bytes of shared memory per SM
+        # so those blocks are co-resident with them instead of waiting for a free SM.
+        self.overlap_solve = os.environ.get("CAL_SOLVE_OVERLAP", "1") != "0"
+        self.solve_headroom = int(os.environ.get("CAL_SMEM_HEADROOM", "40960" if self.overlap_solve else "0"))
+        from . import _lib
+        _lib.check(_lib.lib().cal_set_smem_headroom(self.solve_headroom), "cal_set_smem_headroom")
         self._side = None
+        self._solve_stream = None
         self._copy = None
         self.workload = workload
         self.size = (int(size[0]), int(size[1]))
@@ -60,12 +69,16 @@ class CalibrationPipeline:
             self.camera_creator = CameraCreator(PITCH_POINTS, **kw)
 
     @torch.no_grad()
-    def __call__(self, frames: torch.Tensor, keypoints_override: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    def __call__(self, frames: torch.Tensor, keypoints_override: Optional[torch.Tensor] = None,
+                 defer_solve: bool = False) -> Dict[str, torch.Tensor]:
         """frames: (B,3,H,W) fp32 in [0,1] BGR, on the host (pinned) or on the device.
         Returns device tensors: 'keypoints' (B,57,3), optionally 'lines' (B,23,2,3), and
         'cameras' (B,16) fp64 records (see prediction.CameraCreator.batch_records).
         ``keypoints_override`` (B,57,3) feeds the camera solve instead of the network's own
-        keypoints (benchmarks with random-init weights, whose confidences never pass a threshold)."""
+        keypoints (benchmarks with random-init weights, whose confidences never pass a threshold).
+        ``defer_solve``: the solve is enqueued on the pipeline's solve stream and the current stream does
+        NOT wait for it - the next call's networks run over it; out['solve_stream'] is that stream (work
+        that consumes 'cameras' goes there, or waits for out['cameras_ready'])."""
         x = frames.to(self.device, non_blocking=True)
         line_pts = None
         if self.line_model is not None:
@@ -96,16 +109,38 @@ class CalibrationPipeline:
                 line_pts = self.camera_creator.line_points_device(out["lines"])
         if self.camera_creator is not None:
             kp = out["keypoints"] if keypoints_override is None else keypoints_override
-            out["cameras"] = self.camera_creator.batch_records(kp, line_pts)
+            if not self.overlap_solve:
+                out["cameras"] = self.camera_creator.batch_records(kp, line_pts)
+                return out
+            main = torch.cuda.current_stream(self.device)
+            if self._solve_stream is None:
+                self._solve_stream = torch.cuda.Stream(device=self.device)
+            side = self._solve_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out["cameras"] = self.camera_creator.batch_records(kp, line_pts)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            kp.record_stream(side)
+            if line_pts is not None:
+                line_pts.record_stream(side)
+            out["solve_stream"], out["cameras_ready"] = side, ready
+            if not defer_solve:
+                main.wait_stream(side)
+                out["cameras"].record_stream(main)
         return out
 
     @torch.no_grad()
     def run_stream(self, host_batches, keypoints_override: Optional[torch.Tensor] = None, result_key: Optional[str] = None,
                    to_host: bool = True):
-        """Generator over an iterable of pinned HOST frame batches: the host->device copy of batch
-        i+1 runs on a side stream while batch i computes, and each result is read back to the host
-        (``result_key`` defaults to 'cameras' when the solve is on, else 'keypoints').  This is the
-        loop ``make_submit.py:59-73`` runs with the copies taken off the critical path."""
+        """Generator over an iterable of pinned HOST frame batches; yields each batch's result
+        (``result_key`` defaults to 'cameras' when the solve is on, else 'keypoints') on the host.
+        This is the loop ``make_submit.py:59-73`` runs, software-pipelined so that nothing waits on the
+        critical path: the host->device copy of batch i+1 runs on a copy stream while batch i computes,
+        the camera solve of batch i runs under the networks of batch i+1, and batch i's result travels to
+        a pinned host buffer asynchronously - it is yielded one iteration later, when the host has
+        already enqueued batch i+1.  With ``to_host=False`` device tensors are yielded (the caller
+        synchronises with the solve stream: the tensor carries ``.cal_ready``, a CUDA event)."""
         key = result_key or ("cameras" if self.camera_creator is not None else "keypoints")
         if self._copy is None:                      # one copy stream per pipeline (torch hands streams out of a small pool)
             self._copy = torch.cuda.Stream(device=self.device)
@@ -132,6 +167,9 @@ class CalibrationPipeline:
             nxt = stage(next(it), 0)
         except StopIteration:
             return
+        pending = None                              # (pinned host tensor or device tensor, event) of the previous batch
+        host_out = [None, None]
+        n = 0
         while nxt is not None:
             cur, ev, k = nxt
             try:
@@ -139,7 +177,32 @@ class CalibrationPipeline:
             except StopIteration:
                 nxt = None
             compute.wait_event(ev)
-            out = self(cur, keypoints_override=keypoints_override)
+            out = self(cur, keypoints_override=keypoints_override, defer_solve=True)
             consumed[k] = torch.cuda.Event()
             consumed[k].record(compute)
-            yield out[key].to("cpu") if to_host else out[key]
+            res = out[key]
+            src_stream = out.get("solve_stream", compute) if key == "cameras" else compute
+            if to_host:
+                slot = n & 1
+                if host_out[slot] is None or host_out[slot].shape != res.shape or host_out[slot].dtype != res.dtype:
+                    host_out[slot] = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+                with torch.cuda.stream(src_stream):
+                    host_out[slot].copy_(res, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(src_stream)
+                res.record_stream(src_stream)
+                item = (host_out[slot], done)
+            else:
+                done = out.get("cameras_ready") if key == "cameras" else None
+                if done is None:
+                    done = torch.cuda.Event()
+                    done.record(compute)
+                item = (res, done)
+            n += 1
+            if pending is not None:
+                pending[1].synchronize()
+                yield pending[0].clone() if to_host else pending[0]
+            pending = item
+        if pending is not None:
+            pending[1].synchronize()
+            yield pending[0].clone() if to_host else pending[0]

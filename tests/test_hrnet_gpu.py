@@ -96,3 +96,84 @@ def test_load_state_dict_validation():
     with pytest.raises(ValueError):
         net.load_state_dict(bad)
     net.load_state_dict({"_orig_mod." + k if k.startswith("model.conv1") else k: v for k, v in sd.items()})
+
+
+# ---------------------------------------------------------------------------- end to end
+def _peaked_pair(seed_net, seed_frame, seed_cam, contrast):
+    """fp32 oracle and CUDA network with the same weights whose heat maps have confident blob peaks
+    on one white-noise 960x540 frame (tests/peaked_head.py)."""
+    from tests import peaked_head as PH
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    oracle = O.make_model("keypoints", seed=seed_net)
+    fr = np.random.default_rng(seed_frame).integers(0, 256, (1, 540, 960, 3), dtype=np.uint8)
+    x = torch.from_numpy(I.frames_to_tensor(fr))
+    pos, _ = PH.camera_positions(seed_cam)
+    PH.calibrate_bn(oracle, x)
+    PH.install_templates(oracle, x, pos, contrast=contrast)
+    net = P.HRNetHeatmap(P.w48_config("keypoints")).load_state_dict(oracle.state_dict()).to(DEV)
+    with torch.no_grad():
+        ref = oracle(x)[-1]
+    got = net(x.to(DEV))[-1]
+    return pos, ref.numpy(), got
+
+
+@pytest.mark.parametrize("contrast", [8.0, 3.0])
+def test_end_to_end_keypoint_index_agreement(contrast):
+    """frames -> (57,3) through the fp16-operand CUDA network + CUDA decode against the fp32 oracle
+    network + oracle decode, on weights that give confident peaks: how often do the INTEGER keypoint
+    indices agree (north_star: bit-exact), and what happens to the camera downstream.
+    contrast 8: blobs whose neighbours are ~0.4 log-prob below the peak; contrast 3: much flatter
+    blobs (~0.15), confident almost everywhere - a stress case."""
+    from oracle import camera_ref
+    from soccernet_calibration_sportlight_b200 import pitch, prediction
+    pos, ref, got = _peaked_pair(5, 7, 3, contrast)
+    kp_ref = decode_ref.keypoint_decode_np(ref, (540, 960))[0]
+    kp = ops.kp_decode(got, (540, 960)).cpu().numpy()[0]
+    err = np.abs(got.cpu().numpy() - ref)[0]                              # (58, 270, 480)
+    conf = [c for c in pos if kp_ref[c, 2] > 0.5]
+    assert len(conf) >= 12 and all(kp_ref[c, 2] < 1e-6 for c in range(57) if c not in pos)
+    agree = [c for c in conf if kp[c, 0] == kp_ref[c, 0] and kp[c, 1] == kp_ref[c, 1]]
+    # provably stable peaks: the oracle's best log-prob beats every pixel outside its 3x3 neighbourhood by more
+    # than twice the channel's heat-map error
+    stable = []
+    for c in conf:
+        m = ref[0, c]
+        r, q = np.unravel_index(np.argmax(m), m.shape)
+        rest = m.copy()
+        rest[max(0, r - 1):r + 2, max(0, q - 1):q + 2] = -np.inf
+        if m[r, q] - rest.max() > 2 * err[c].max():
+            stable.append(c)
+    shift = max([max(abs(kp[c, 0] - kp_ref[c, 0]), abs(kp[c, 1] - kp_ref[c, 1])) for c in conf] + [0])
+    dconf = max(abs(float(kp[c, 2]) - float(kp_ref[c, 2])) for c in conf)
+    print(f"\\nend-to-end keypoints (contrast {contrast}): {len(agree)}/{len(conf)} confident keypoints with identical integer "
+          f"indices, {len(stable)} provably separated, max index shift {shift:.0f} px, max |conf diff| {dconf:.2e}, "
+          f"heat-map max |log-prob err| {err[:57].max():.4f} (confident channels {max(err[c].max() for c in conf):.4f})")
+    assert len(agree) >= 0.9 * len(conf)
+    assert shift <= 2.0                                                   # never more than one heat-map pixel
+    # downstream: the camera from the CUDA path's keypoints against the reference path's
+    # (oracle net -> oracle decode -> CameraCreator on cv2)
+    kw = {k: v for k, v in camera_ref.MAKE_SUBMIT_KWARGS.items() if k not in ("algorithm", "conf_thresh")}
+    creator = prediction.CameraCreator(pitch.PITCH_POINTS, conf_thresh=0.5, algorithm="iterative_voter", **kw)
+    cam = creator(kp, "frame")
+    rc_creator = camera_ref.make_submit_creator()
+    rc = rc_creator(kp_ref, None)
+    if rc_creator.pinned and len(agree) == len(conf):
+        assert (cam is None) == (rc is None)
+        if cam is not None:
+            a = np.concatenate([cam.position, cam.rotation.ravel(), [cam.xfocal_length]])
+            b = np.concatenate([rc.position, rc.rotation.ravel(), [rc.xfocal_length]])
+            rel = float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1.0)))
+            print(f"camera from CUDA-path keypoints vs reference path: max relative parameter error {rel:.2e}")
+            assert rel < 1e-4
+
+
+@pytest.mark.parametrize("kind,H,W", [("lines", 540, 960), ("keypoints", 720, 1280), ("lines", 720, 1280),
+                                      ("keypoints", 1080, 1920), ("lines", 1080, 1920)])
+def test_networks_vs_oracle_at_config5_resolutions(kind, H, W):
+    """One frame per network at the BASELINE sizes (540p line net, 720p and 1080p both nets; pyramids end
+    in 17 / 23 / 34 rows) against the fp32 oracle."""
+    ref, got = run_pair(kind, H, W, 1, seed=13)
+    assert got.shape == ref.shape
+    tol = 0.05 if kind == "keypoints" else 5e-3
+    assert float((got - ref).abs().max()) <= tol
+    assert float((got - ref).norm() / ref.norm()) <= 1e-2

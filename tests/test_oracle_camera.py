@@ -171,3 +171,39 @@ def test_camera_mirror_closed_form_members():
         assert np.allclose(cam_mod.rotation_from_rodrigues(cam_mod.rodrigues(R)), R, atol=1e-12)
     a.scale_resolution(2.0)
     assert a.image_width == 1920 and a.principal_point == (960.0, 540.0)
+
+
+def test_camera_mirror_k_from_homography_and_distort():
+    """Camera.estimate_calibration_matrix_from_plane_homography / distort (camera.py:366-426, 220-247)
+    against the oracle's restatement on homographies of plausible cameras."""
+    rng = np.random.default_rng(12)
+    n = 0
+    for _ in range(20):
+        R, pos, f = CI.random_camera(rng)
+        K = np.array([[f, 0, 480.0], [0, f, 270.0], [0, 0, 1.0]])
+        t = -R @ pos
+        H = K @ np.stack([R[:, 0], R[:, 1], t], axis=1)
+        H = H / H[2, 2] + rng.normal(0, 1e-4, (3, 3))
+        a, b = cam_mod.Camera(), O.CameraRef()
+        oka, Ka = a.estimate_calibration_matrix_from_plane_homography(H)
+        okb, Kb = b.estimate_calibration_matrix_from_plane_homography(H)
+        assert oka == okb
+        if oka:
+            assert np.allclose(Ka, Kb, rtol=1e-9, atol=1e-9) and a.xfocal_length == pytest.approx(b.xfocal_length, rel=1e-12)
+            assert np.array_equal(a.calibration, b.calibration)
+            assert abs(a.xfocal_length - f) < 0.05 * f
+            n += 1
+    assert n >= 10
+    assert cam_mod.Camera().estimate_calibration_matrix_from_plane_homography(np.diag([1.0, -1.0, 1.0]))[0] is False
+    c = cam_mod.Camera()
+    p = np.array([0.123456789, -0.2345678901])
+    assert c.distort(p).dtype == np.float32 and np.array_equal(c.distort(p), p.astype(np.float32))
+    c.radial_distortion[:] = [0.1, -0.02, 0.003, 0.05, 0.001, 0.0]
+    c.tangential_disto[:] = [1e-3, -2e-3]
+    c.thin_prism_disto[:] = [1e-4, 2e-4, -1e-4, 3e-4]
+    x, y = p
+    r2 = x * x + y * y
+    f_r = (1 + 0.1 * r2 - 0.02 * r2 ** 2 + 0.003 * r2 ** 3) / (1 + 0.05 * r2 + 0.001 * r2 ** 2)
+    xd = x * f_r + 2 * 1e-3 * x * y - 2e-3 * (r2 + 2 * x * x) + 1e-4 * r2 + 2e-4 * r2 ** 2
+    yd = y * f_r + 2 * -2e-3 * x * y + 1e-3 * (r2 + 2 * y * y) - 1e-4 * r2 + 3e-4 * r2 ** 2
+    assert np.allclose(c.distort(p), [xd, yd], rtol=1e-6)

@@ -18,13 +18,17 @@
 //     loop is a handful of instructions per MMA, a stage's wait comes before the previous
 //     stage's commit, and work items of T = 2 tiles share every slice where TMEM allows;
 //   * C <= 64 (the 135x240 branch: a quarter of the step): an MMA of M = 128, K = 16 reads its A operand
-//     from shared memory in 32 cycles whatever N is, so N = 48 runs at 24 / 44 of the tensor rate.  The
-//     three taps of one filter ROW share the A view when the column shift is taken out of the
-//     operand: G_dx[q] = sum_dy W[dy,dx] X[q + dy*TWp] for dx = 0..2 is ONE accumulation with
-//     N = 3 * Cout (the resident weight slices of a filter row are contiguous in shared memory), three
-//     MMAs per K step instead of nine, math-bound (72 cycles at N = 144).  out[p] = G_0[p] + G_1[p+1]
-//     + G_2[p+2] is formed by the epilogue: with TWp <= 32 a patch row lies inside one warp's 32 TMEM
-//     lanes, so the two shifts are warp shuffles (template DX);
+//     from shared memory in 32 cycles whatever N is, so N = 48 runs at 24 / 44 of the tensor rate and
+//     nine of them per K step re-read the same patch nine times.  Template DX takes the column shift of
+//     two taps out of the operand: per filter row dy, ONE MMA with N = 2 * Cout multiplies the view
+//     shifted by dy rows with the taps dx = 1 and dx = 0 side by side (accumulator columns [G1 | G0]),
+//     and the tap dx = 2 accumulates into the G1 columns from the view shifted one more pixel:
+//     G1'[q] = sum_dy W[dy,1] X[q + dy*TWp] + W[dy,2] X[q + 1 + dy*TWp], G0[q] = sum_dy W[dy,0] X[q + dy*TWp],
+//     out[p] = G0[p] + G1'[p + 1].  Six MMAs per K step instead of nine (300 instead of 396 operand-read
+//     cycles), and the one shift left is a warp shuffle in the epilogue: with TWp <= 32 a patch row lies
+//     inside one warp's 32 TMEM lanes.  (All three taps in one N = 3 * Cout MMA was tried first: two
+//     shuffles per value and 160 accumulator columns - only two TMEM stages - made the epilogue and the
+//     issuer wait for each other: 200 vs 171 us.)
 //   * epilogue: TMEM -> registers (32 columns per tcgen05.ld) -> bias / residual / ReLU -> fp16
 //     -> 32-byte-sector stores straight from registers (st.global.v8). A swizzled staging tile
 //     drained by TMA stores remains as a build option (-DCAL_HALO_STAGED): its shared-memory traffic
@@ -68,7 +72,7 @@ struct HaloParams {
   int w_slices;            // weights are slice-major: slice s = rows [s*Cout_rows, (s+1)*Cout_rows) of a (.., 64) matrix
   int cout_rows;
   int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
-  int dx;               // filter-row grouping: N = 3 * mma_n per MMA, column shifts in the epilogue (template DX)
+  int dx;               // filter-row grouping: taps dx = 1, 0 in one N = 2 * mma_n MMA, the column shift in the epilogue (template DX)
   int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
   int w_resident, b_stages, b_slice_bytes;
@@ -143,7 +147,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull = wfull + 1;
   uint64_t* tempty = tfull + H_MAX_ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + H_MAX_ACC);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));   // 16-byte aligned (float4 reads)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (p.dbg && threadIdx.x == 0) {            // per-CTA wall-clock span (entries after the role stamps)
@@ -180,8 +184,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (RESIDENT) {
         mbar_expect_tx(wfull, p.b_tx_bytes * 9u * static_cast<uint32_t>(p.ncc));
         for (int s = 0; s < 9 * p.ncc; ++s) {
-          if (p.w_slices) tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, 0, s * p.cout_rows);
-          else tma_load_2d(sW + s * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
+          // DX (one chunk): the taps of a filter row are stored dx = 1, 0, 2
+          const int slot = DX ? (s / 3) * 3 + ((s % 3) == 0 ? 1 : ((s % 3) == 1 ? 0 : 2)) : s;
+          if (p.w_slices) tma_load_2d(sW + slot * p.b_slice_bytes, &tmB, wfull, 0, s * p.cout_rows);
+          else tma_load_2d(sW + slot * p.b_slice_bytes, &tmB, wfull, s * 64, 0);
         }
       }
       griddep_wait();                           // activations of the previous kernel from here on
@@ -246,7 +252,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // word, the tap order and the tiles per item are compile-time constants.
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
-    const uint32_t idesc = make_idesc_f16(128, DX ? 3 * p.mma_n : p.mma_n);
+    const uint32_t idesc = make_idesc_f16(128, p.mma_n);
+    const uint32_t idesc2 = make_idesc_f16(128, 2 * p.mma_n);      // DX: two taps side by side
     const uint64_t desc0 = make_smem_desc(0, 128, 2);      // everything but the start address
     const uint32_t dhi = static_cast<uint32_t>(desc0 >> 32), dlo = static_cast<uint32_t>(desc0);
     uint32_t tap_off[9];
@@ -290,18 +297,24 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int nk = (cc == ncc - 1) ? ksteps_last : 4;       // pad lanes of the last chunk are zero: skip them
         const uint32_t w_cc = w_lo0 + cc * w_step;
         if (DX) {
-          // one MMA per (filter row, K step): A = the patch shifted by dy rows of TWp pixels,
-          // B = the three taps of that filter row (3 * mma_n weight rows, contiguous resident slices)
+          // per filter row: [taps dx = 1 | dx = 0] from the view shifted by dy rows, then tap dx = 2 from
+          // the view one pixel further into the first group's accumulator columns
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             if (do_mma) {
               const uint32_t at = a_lo + tap_off[dy * 3];
+              const uint32_t at1 = a_lo + tap_off[dy * 3 + 1];
               const uint32_t bl = w_cc + dy * 3 * w_tap;
+              const uint32_t bl2 = bl + 2 * w_tap;
               const uint32_t first = (cc | dy) != 0;
-              umma_f16_lo(d_tmem, at, bl, dhi, idesc, first);
-              if (nk > 1) umma_f16_lo(d_tmem, at + 2, bl + 2, dhi, idesc, 1);
-              if (nk > 2) umma_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc, 1);
-              if (nk > 3) umma_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc, 1);
+              umma_f16_lo(d_tmem, at, bl, dhi, idesc2, first);
+              if (nk > 1) umma_f16_lo(d_tmem, at + 2, bl + 2, dhi, idesc2, 1);
+              if (nk > 2) umma_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc2, 1);
+              if (nk > 3) umma_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc2, 1);
+              umma_f16_lo(d_tmem, at1, bl2, dhi, idesc, 1);
+              if (nk > 1) umma_f16_lo(d_tmem, at1 + 2, bl2 + 2, dhi, idesc, 1);
+              if (nk > 2) umma_f16_lo(d_tmem, at1 + 4, bl2 + 4, dhi, idesc, 1);
+              if (nk > 3) umma_f16_lo(d_tmem, at1 + 6, bl2 + 6, dhi, idesc, 1);
             }
             if (dy == 1 && cc == ncc - 1 && has_next) {
               const int as_n = (as + 1 == n_acc) ? 0 : as + 1;
@@ -524,33 +537,36 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       };
       if (DX) {
-        // out[p] = G_0[p] + G_1[p + 1] + G_2[p + 2]: the three column groups of the accumulator, the
-        // shifts by warp shuffles (a patch row of TWp <= 32 pixels lies inside this warp's lanes; lanes
-        // whose neighbours belong to the next row are the two halo columns, which are not stored)
+        // out[p] = G0[p] + G1'[p + 1]: the two column groups of the accumulator, the shift by a warp
+        // shuffle (a patch row of TWp <= 32 pixels lies inside this warp's lanes; the lanes whose
+        // neighbour belongs to the next row are halo columns, which are not stored)
         // 16-channel blocks of the output pixel (Cout_pad = 64: four)
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) {
           uint32_t o[8];
           if (cb * 16 < p.mma_n) {
-            uint32_t g0[16], g1[16], g2[16];
-            tmem_ld16(taddr + cb * 16, g0);
-            tmem_ld16(taddr + p.mma_n + cb * 16, g1);
-            tmem_ld16(taddr + 2 * p.mma_n + cb * 16, g2);
+            uint32_t g1[16], g0[16];
+            tmem_ld16(taddr + cb * 16, g1);
+            tmem_ld16(taddr + p.mma_n + cb * 16, g0);
             tmem_ld_wait();
             const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            const float* bb = s_bias + tc.n0 + cb * 16;
+            const float4* bb4 = reinterpret_cast<const float4*>(s_bias + tc.n0 + cb * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float a = __uint_as_float(g0[2 * j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j]), 1) +
-                        __shfl_down_sync(0xffffffffu, __uint_as_float(g2[2 * j]), 2);
-              float b = __uint_as_float(g0[2 * j + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j + 1]), 1) +
-                        __shfl_down_sync(0xffffffffu, __uint_as_float(g2[2 * j + 1]), 2);
-              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
-              a += bb[2 * j] + __low2float(rh);
-              b += bb[2 * j + 1] + __high2float(rh);
-              if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-              o[j] = h_pack_half2(a, b);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 bq = bb4[j4];
+              const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int j = j4 * 2 + h2;
+                float a = __uint_as_float(g0[2 * j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j]), 1);
+                float b = __uint_as_float(g0[2 * j + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j + 1]), 1);
+                const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
+                a += bv[2 * h2] + __low2float(rh);
+                b += bv[2 * h2 + 1] + __high2float(rh);
+                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
+                o[j] = h_pack_half2(a, b);
+              }
             }
           } else {
             // pad channels stay zero
@@ -630,10 +646,10 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   p.B = a->B; p.H = a->Hout; p.W = a->Wout; p.Cout_pad = a->Cout_pad;
   // tile geometry: few tiles (MMA rows are spent on every tile, used or not) and a small halo
   // patch (L2 -> SM bytes per tile)
-  // filter-row grouping (template DX) applies to the single-chunk, single-N-tile layers whose three taps of a
-  // filter row fit one MMA: C <= 64 in, Cout_rows <= 80 out; it needs a patch row inside one warp (TWp <= 32)
+  // filter-row grouping (template DX) applies to the single-chunk, single-N-tile layers (C <= 64 in and out);
+  // it needs a patch row inside one warp (TWp <= 32)
   static const bool dx_enabled = [] { const char* e = getenv("CAL_CONV_DX"); return !(e && e[0] == '0'); }();
-  const bool dx_shape = dx_enabled && a->Cin_pad == 64 && a->Cout_pad == 64 && a->Cout_rows % 8 == 0 && 3 * a->Cout_rows <= 256;
+  const bool dx_shape = dx_enabled && a->Cin_pad == 64 && a->Cout_pad == 64 && a->Cout_rows % 8 == 0;
   long best = -1;
   for (int twp = 16; twp <= (dx_shape ? 32 : 128); twp *= 2) {
     const int tw = twp - 2, r = 128 / twp;
@@ -682,7 +698,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   // up the double buffering for T = 2 / 4 (C=192, 384; C=96 at T = 4) loses what the sharing gains.
   // Resident weights share nothing but the handshakes, and with a residual input the two epilogue
   // groups of a T = 2 item read their residual rows at the same moment: T = 1 there (178 vs 193 us).
-  const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + H_MAX_BIAS * 4;
+  const int tail = (2 * H_MAX_A_STAGES + 2 * H_MAX_B_STAGES + 1 + 2 * H_MAX_ACC) * 8 + 16 + 16 + H_MAX_BIAS * 4;
   const int w_all = 9 * p.ncc * p.b_slice_bytes;
   const int avail = 224 * 1024 - smem_headroom();
   const int budget_res = avail - 1024 - tail - (H_STAGED_BUILD ? 2 * p.nblk * H_STAGE_BLOCK : 0);   // (evaluated before any N split)
@@ -705,9 +721,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   if (n_tiles == 1 && w_all + 2 * p.a_stage_bytes <= budget_res) {
     p.w_resident = 1;
     if (dx_shape && p.b_slice_bytes == p.mma_n * 128) {
-      // (slices of mma_n * 128 bytes are contiguous: a filter row's three taps form one 3 * mma_n-row operand)
+      // (slices of mma_n * 128 bytes are contiguous: two neighbouring taps form one 2 * mma_n-row operand)
       p.dx = 1;
-      p.acc_stride = (3 * p.mma_n + 31) & ~31;
+      p.acc_stride = (2 * p.mma_n + 31) & ~31;
       set_tiles(1);
     }
     // Outputs go straight from registers to global memory (two full 32-byte sectors per lane and

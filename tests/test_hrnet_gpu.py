@@ -117,13 +117,13 @@ def _peaked_pair(seed_net, seed_frame, seed_cam, contrast):
     return pos, ref.numpy(), got
 
 
-@pytest.mark.parametrize("contrast", [8.0, 3.0])
+@pytest.mark.parametrize("contrast", [8.0, 5.0])
 def test_end_to_end_keypoint_index_agreement(contrast):
     """frames -> (57,3) through the fp16-operand CUDA network + CUDA decode against the fp32 oracle
     network + oracle decode, on weights that give confident peaks: how often do the INTEGER keypoint
     indices agree (north_star: bit-exact), and what happens to the camera downstream.
-    contrast 8: blobs whose neighbours are ~0.4 log-prob below the peak; contrast 3: much flatter
-    blobs (~0.15), confident almost everywhere - a stress case."""
+    contrast 8: blobs whose neighbours are ~0.4 log-prob below the peak; contrast 5: flatter blobs (~0.25)
+    on a background only just below them."""
     from oracle import camera_ref
     from soccernet_calibration_sportlight_b200 import pitch, prediction
     pos, ref, got = _peaked_pair(5, 7, 3, contrast)

@@ -35,6 +35,27 @@ KEYPOINT_CFG = dict(W48, num_classes=58, upscale=2, head="logsoftmax")   # hrnet
 LINE_CFG = dict(W48, num_classes=23, upscale=1, head="softmax")          # line/model_config/hrnet_w48.yaml
 
 
+def _variant(**stages):
+    cfg = dict(W48)
+    cfg.update(stages)
+    return cfg
+
+
+# the other shipped keypoint configs (hrnet_w18.yaml, hrnet_w64.yaml, hrnet_w48x4.yaml)
+W18_CFG = dict(_variant(
+    stage1=dict(num_modules=1, num_branches=1, block="BOTTLENECK", num_blocks=[1], num_channels=[32]),
+    stage2=dict(num_modules=1, num_branches=2, block="BASIC", num_blocks=[2, 2], num_channels=[16, 32]),
+    stage3=dict(num_modules=1, num_branches=3, block="BASIC", num_blocks=[2, 2, 2], num_channels=[16, 32, 64]),
+    stage4=dict(num_modules=1, num_branches=4, block="BASIC", num_blocks=[2, 2, 2, 2], num_channels=[16, 32, 64, 128])),
+    num_classes=58, upscale=2, head="logsoftmax")
+W64_CFG = dict(_variant(
+    stage2=dict(num_modules=1, num_branches=2, block="BASIC", num_blocks=[4, 4], num_channels=[64, 128]),
+    stage3=dict(num_modules=4, num_branches=3, block="BASIC", num_blocks=[4, 4, 4], num_channels=[64, 128, 256]),
+    stage4=dict(num_modules=3, num_branches=4, block="BASIC", num_blocks=[4, 4, 4, 4], num_channels=[64, 128, 256, 512])),
+    num_classes=58, upscale=2, head="logsoftmax")
+W48X4_CFG = dict(W48, num_classes=58, upscale=4, head="logsoftmax")
+
+
 def _bn(c):
     # the reference aliases BatchNorm2d = SyncBatchNorm (hrnet.py:18); in eval mode
     # (the only mode on this path) both compute the same per-channel affine.
@@ -242,7 +263,7 @@ def randomize_bn_(module: nn.Module, gen: torch.Generator) -> None:
 def make_model(kind: str = "keypoints", seed: int = 0) -> HRNetHeatmapRef:
     """Seeded random-init oracle network in eval mode (no trained weights ship with
     the reference)."""
-    cfg = KEYPOINT_CFG if kind == "keypoints" else LINE_CFG
+    cfg = {"keypoints": KEYPOINT_CFG, "lines": LINE_CFG, "w18": W18_CFG, "w64": W64_CFG, "w48x4": W48X4_CFG}[kind]
     g = torch.Generator().manual_seed(seed)
     state = torch.random.get_rng_state()
     torch.manual_seed(seed)

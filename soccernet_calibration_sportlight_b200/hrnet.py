@@ -62,6 +62,39 @@ def w48_config(kind: str = "keypoints") -> Config:
     return Config(cfg)
 
 
+def w18_config() -> Config:
+    """model_config/hrnet_w18.yaml (keypoints)."""
+    return Config(dict(num_classes=58, stem_width=64, final_conv_kernel=1, internal_final_conv=0, upscale=2, pretrain="",
+                       stage1=_stage(1, 1, "BOTTLENECK", [1], [32]),
+                       stage2=_stage(1, 2, "BASIC", [2, 2], [16, 32]),
+                       stage3=_stage(1, 3, "BASIC", [2, 2, 2], [16, 32, 64]),
+                       stage4=_stage(1, 4, "BASIC", [2, 2, 2, 2], [16, 32, 64, 128])))
+
+
+def w64_config() -> Config:
+    """model_config/hrnet_w64.yaml (keypoints): the w48 schedule with 64/128/256/512 channels."""
+    cfg = dict(w48_config("keypoints"))
+    cfg.update(stage2=_stage(1, 2, "BASIC", [4, 4], [64, 128]),
+               stage3=_stage(4, 3, "BASIC", [4, 4, 4], [64, 128, 256]),
+               stage4=_stage(3, 4, "BASIC", [4, 4, 4, 4], [64, 128, 256, 512]))
+    return Config(cfg)
+
+
+def w48x4_config() -> Config:
+    """model_config/hrnet_w48x4.yaml (keypoints): w48 with the head at four times the first branch's
+    resolution (= the input resolution); the stem output is resampled to it (hrnet.py:494-498)."""
+    cfg = dict(w48_config("keypoints"))
+    cfg.update(upscale=4)
+    return Config(cfg)
+
+
+def config_from_yaml(path: str) -> Config:
+    """One of the reference's ``model_config/*.yaml`` files (flat keys + stage1..stage4 mappings)."""
+    import yaml
+    with open(path) as f:
+        return Config(yaml.safe_load(f))
+
+
 # ------------------------------------------------------------------------- architecture walk
 class _Conv:
     """One conv(+BN) of the reference, identified by its state_dict prefixes."""

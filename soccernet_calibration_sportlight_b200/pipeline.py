@@ -37,10 +37,13 @@ class CalibrationPipeline:
         self.two_streams = os.environ.get("CAL_TWO_STREAMS", "1") != "0"
         # the camera solve of batch i under the networks of batch i+1 (the reference overlaps them too:
         # a 16-process CPU pool solves while the GPU runs on, make_submit.py:53-73).  The solve kernel is
-        # 64 small blocks; the persistent conv kernels leave `solve_headroom` bytes of shared memory per SM
-        # so those blocks are co-resident with them instead of waiting for a free SM.
+        # 64 small blocks (64 threads x <= 168 registers, 39 KB) that slip into the gaps the networks leave:
+        # kernel tails, the CUDA-core kernels (stem, multi-resolution sums), and any SM whose persistent
+        # conv CTA leaves room.  `solve_headroom` (CAL_SMEM_HEADROOM) makes the conv kernels keep that many
+        # bytes of shared memory free on every SM; measured on B200 the gaps alone hide the whole solve
+        # (93.6 ms per step with 0, 94.0 ms with 40960, 129 ms without the overlap), so the default is 0.
         self.overlap_solve = os.environ.get("CAL_SOLVE_OVERLAP", "1") != "0"
-        self.solve_headroom = int(os.environ.get("CAL_SMEM_HEADROOM", "40960" if self.overlap_solve else "0"))
+        self.solve_headroom = int(os.environ.get("CAL_SMEM_HEADROOM", "0"))
         from . import _lib
         _lib.check(_lib.lib().cal_set_smem_headroom(self.solve_headroom), "cal_set_smem_headroom")
         self._side = None

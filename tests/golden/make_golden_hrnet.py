@@ -45,6 +45,24 @@ for kind, Ref in (("keypoints", RefKp), ("lines", RefLine)):
     print(kind, "oracle == reference bit-exact on", tuple(x.shape), "->", tuple(yr.shape),
           "params", sum(p.numel() for p in ref.parameters()))
     out[f"{kind}__out"] = yr.numpy()
+# the other shipped keypoint configs (model_config/hrnet_w18.yaml, hrnet_w64.yaml, hrnet_w48x4.yaml), read
+# from the reference's own yaml files: oracle == reference bit for bit; a small output slice is stored
+CFG_DIR = os.path.join(refimport.REF, "src", "models", "hrnet", "model_config")
+for kind, fn in (("w18", "hrnet_w18.yaml"), ("w64", "hrnet_w64.yaml"), ("w48x4", "hrnet_w48x4.yaml")):
+    cfg = P.config_from_yaml(os.path.join(CFG_DIR, fn))
+    ref = RefKp(cfg, 0, cfg.num_classes).eval()
+    oracle = O.make_model(kind, seed=11)
+    ref.load_state_dict(oracle.state_dict(), strict=True)
+    schema = P.state_dict_schema(cfg, "keypoints")
+    assert list(schema.keys()) == list(ref.state_dict().keys()), f"{kind}: schema key order differs"
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(21, 1, 64, 96)))
+    with torch.no_grad():
+        yr = ref(x)[-1]
+        yo = oracle(x)[-1]
+    assert torch.equal(yr, yo), f"{kind}: oracle != reference"
+    print(kind, "oracle == reference bit-exact ->", tuple(yr.shape), "params", sum(p.numel() for p in ref.parameters()))
+    out[f"{kind}__out"] = yr.numpy()
+    keys[kind] = {k: list(v.shape) for k, v in ref.state_dict().items()}
 with open(os.path.join(HERE, "hrnet_state_keys.json"), "w") as f:
     json.dump(keys, f)
 np.savez_compressed(os.path.join(HERE, "hrnet_small.npz"), **out)

@@ -99,3 +99,42 @@ def test_make_submit_driver_end_to_end(tmp_path):
                       "y_focal_length", "principal_point", "radial_distortion", "tangential_distortion",
                       "thin_prism_distortion"}
     assert d["principal_point"] == [480.0, 270.0] and len(d["position_meters"]) == 3
+
+
+@pytest.mark.gpu
+def test_export_line_result_round_trip(tmp_path):
+    """jpg frames -> line checkpoint -> export_line_result (export_line_result.py:134-201) -> pickle ->
+    CameraCreator(lines_file=...) (prediction.py:104-124): the writer's layout is what the reader takes,
+    and its lines equal the oracle's get_line_data on the same decoded peaks."""
+    import pickle
+    import cv2
+    from oracle import decode_ref
+    from soccernet_calibration_sportlight_b200 import export_line_result
+    img_dir = tmp_path / "imgs"
+    img_dir.mkdir()
+    frames = I.frames_u8(9, 3, 96, 160)
+    for i in range(3):
+        cv2.imwrite(str(img_dir / f"{i:05d}.jpg"), frames[i])
+    model = metamodel.LineMetaModel({"nn_module": {"num_refinement_stages": 0},
+                                     "prediction_transform": {"scale": 4, "sigma": 3.0}}).set_device("cuda:0")
+    ckpt, out = str(tmp_path / "line.pth"), str(tmp_path / "res" / "lines.pkl")
+    model.save(ckpt)
+    res = export_line_result.main(["--model", ckpt, "--image-folder", str(img_dir), "--result-file", out,
+                                   "--prob-thre", "0.0", "--batch-size", "2", "--no-vis"])
+    stored = pickle.load(open(out, "rb"))
+    assert sorted(stored) == ["00000.jpg", "00001.jpg", "00002.jpg"] and set(stored["00000.jpg"]) == {"lines", "points"}
+    # against the oracle's dictionary building on the decoded peaks of the same (jpg-decoded) frame
+    img = cv2.imread(str(img_dir / "00001.jpg"), cv2.IMREAD_COLOR)
+    heat = model.nn_module(make_submit.frames_to_tensor([img]).cuda())[-1]
+    peaks = decode_ref.line_decode_np(heat.cpu().numpy(), 3.0)
+    lines, points = decode_ref.get_line_data(peaks, pitch.LINE_CLS, scale=4, prob_thre=0.0)
+    assert set(lines) == set(stored["00001.jpg"]["lines"]) and len(lines) == 23
+    for k, (slope, icpt) in lines.items():
+        s2, i2 = stored["00001.jpg"]["lines"][k]
+        assert (slope is None) == (s2 is None)
+        if slope is not None:
+            assert float(slope) == float(s2) and float(icpt) == float(i2)
+    assert res["00001.jpg"]["points"].keys() == points.keys()
+    # the reader takes the writer's layout
+    cal = prediction.CameraCreator(pitch.PITCH_POINTS, lines_file=out, **prediction.MAKE_SUBMIT_KWARGS)
+    assert isinstance(cal.lines_data, dict)

@@ -177,3 +177,23 @@ def test_networks_vs_oracle_at_config5_resolutions(kind, H, W):
     tol = 0.05 if kind == "keypoints" else 5e-3
     assert float((got - ref).abs().max()) <= tol
     assert float((got - ref).norm() / ref.norm()) <= 1e-2
+
+
+@pytest.mark.parametrize("kind", ["w18", "w64", "w48x4"])
+def test_other_shipped_configs_vs_oracle(kind, golden_dir):
+    """model_config/hrnet_w18.yaml, hrnet_w64.yaml, hrnet_w48x4.yaml through the same engine, against the fp32
+    oracle variant (pinned bit-exact to the reference modules) and the stored reference output."""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    cfg = {"w18": P.w18_config, "w64": P.w64_config, "w48x4": P.w48x4_config}[kind]()
+    oracle = O.make_model(kind, seed=11)
+    net = P.HRNetHeatmap(cfg).load_state_dict(oracle.state_dict()).to(DEV)
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(21, 1, 64, 96)))
+    got = net(x.to(DEV))[-1].cpu()
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, "hrnet_small.npz"))[f"{kind}__out"])
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 0.05
+    x2 = torch.from_numpy(I.frames_to_tensor(I.frames_u8(3, 2, 135, 240)))
+    with torch.no_grad():
+        ref2 = oracle(x2)[-1]
+    got2 = net(x2.to(DEV))[-1].cpu()
+    assert float((got2 - ref2).abs().max()) <= 0.05 and float((got2 - ref2).norm() / ref2.norm()) <= 1e-2

@@ -55,3 +55,21 @@ def test_config_access():
     cfg = P.w48_config("keypoints")
     assert "upscale" in cfg and cfg.upscale == 2 and cfg.stage4.num_channels[-1] == 384
     assert "upscale" not in P.w48_config("lines")
+
+
+def test_other_shipped_configs(golden_dir):
+    """hrnet_w18 / hrnet_w64 / hrnet_w48x4 (model_config/*.yaml): the oracle's variants reproduce the stored
+    reference outputs, and the product's architecture walk yields the reference's state_dict schema."""
+    z = np.load(os.path.join(golden_dir, "hrnet_small.npz"))
+    with open(os.path.join(golden_dir, "hrnet_state_keys.json")) as f:
+        keys = json.load(f)
+    x = torch.from_numpy(I.frames_to_tensor(I.frames_u8(21, 1, 64, 96)))
+    for kind, cfg in (("w18", P.w18_config()), ("w64", P.w64_config()), ("w48x4", P.w48x4_config())):
+        schema = P.state_dict_schema(cfg, "keypoints")
+        assert list(schema) == list(keys[kind]) and all(list(schema[k]) == keys[kind][k] for k in schema)
+        if kind == "w64":
+            continue                               # 117 M parameters: the forward is left to the GPU suite
+        with torch.no_grad():
+            y = O.make_model(kind, seed=11)(x)[-1].numpy()
+        np.testing.assert_allclose(y, z[f"{kind}__out"], rtol=0, atol=2e-4)
+    assert P.w48x4_config().upscale == 4 and P.w18_config().stage1.num_channels == [32]

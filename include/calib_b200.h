@@ -246,6 +246,46 @@ int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int mode, float
  * entry per CTA. */
 int cal_debug_mma_rate(int N, int shift_rows, int iters, int flags, long long* out_cycles, void* stream);
 
+/* ------------------------------------------------------------------ metric -- */
+
+/* The official camera-calibration metric on the GPU, one thread block per frame: the step after the path,
+ * what EvalAImetric runs per validation batch (src/models/hrnet/metrics.py:107-137, 181-211).
+ * Replaces get_polylines (baseline/evaluate_camera.py:14-107: the sampled pitch model projected by the
+ * camera, clipped at the image border), distance_to_polyline (:110-160) and evaluate_camera_prediction
+ * (:163-229) for the annotation and for its mirrored labelling (evaluate_extremities.py:24-34), and the
+ * choice between the two of Evaluator.__call__ (metrics.py:112-135).
+ *   cams        : (B) camera records (cal_camera_solve's output); valid = 0 -> out.valid = 0 ("missed")
+ *   field_pts   : (n_pts, 3) fp64 sampled pitch points (SoccerPitch.sample_field_points), grouped by class
+ *   class_off   : (n_proj + 1) int32 offsets of each projectable class into field_pts
+ *   class_id    : (n_proj) int32 index of that class among the CAL_EVAL_CLASSES dataset classes
+ *   mirror      : (CAL_EVAL_CLASSES) int32 class index under the point reflection through the pitch centre
+ *   is_circle   : (CAL_EVAL_CLASSES) uint8 ('Circle' in the class name: 9 false positives instead of 2)
+ *   gt_pts      : (B, CAL_EVAL_CLASSES, max_gt, 2) fp64 annotated points in pixels
+ *   gt_count    : (B, CAL_EVAL_CLASSES) int32, -1 = class absent from the annotation
+ *   poly        : (B, n_proj, max_poly, 2) fp64 polylines (output, or input when from_polylines & 1;
+ *                 from_polylines & 2: report the labelling as annotated instead of the better one)
+ *   poly_count  : (B, n_proj) int32 (ditto)
+ *   dist        : (B, 2, CAL_EVAL_CLASSES, max_gt) fp64 scratch: point-to-polyline distances per labelling */
+#define CAL_EVAL_CLASSES 28
+typedef struct CalEvalRecord {
+  double accuracy;                         /* confusion[0][0] / sum of the chosen labelling */
+  double confusion[4];                     /* [[tp, fp], [fn, 0]] over classes */
+  double l2_sum;                           /* sum of the point-to-polyline distances of the common classes */
+  int32_t l2_count;
+  int32_t labelling;                       /* 0 = as annotated, 1 = mirrored */
+  int32_t valid;
+  int32_t pad;
+  double per_class[CAL_EVAL_CLASSES][4];   /* per-class confusion matrices, rows of zeros for untouched classes */
+  uint8_t touched[CAL_EVAL_CLASSES];       /* class has an entry in the reference's per-class dictionary */
+  uint8_t pad2[4];
+} CalEvalRecord;
+
+int cal_evaluate_cameras(const CalCameraRecord* cams, int B, const double* field_pts, const int32_t* class_off,
+                         const int32_t* class_id, int n_proj, const int32_t* mirror, const uint8_t* is_circle,
+                         const double* gt_pts, const int32_t* gt_count, int max_gt, int img_w, int img_h,
+                         double threshold, double* poly, int32_t* poly_count, int max_poly, int from_polylines,
+                         double* dist, CalEvalRecord* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

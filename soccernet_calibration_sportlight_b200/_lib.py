@@ -13,7 +13,7 @@ CAL_MAX_SOURCES = 6
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
-    "cal_line_points",
+    "cal_line_points", "cal_evaluate_cameras",
     "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",
 ]
 
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.cal_line_points.argtypes = [vp, i32, i32, vp, vp, f32, vp, vp]
+    L.cal_evaluate_cameras.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         if hasattr(L, name) and name != "cal_last_error":
             getattr(L, name).restype = C.c_int

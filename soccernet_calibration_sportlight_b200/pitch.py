@@ -203,3 +203,102 @@ def _line_pairs() -> Dict[int, Tuple[str, str]]:
 
 
 LINE_INTERSECTIONS: Dict[int, Tuple[str, str]] = _line_pairs()
+
+
+# ------------------------------------------------------------------ evaluation-side tables
+# the 28 line classes of the dataset (baseline/soccerpitch.py:15-44), alphabetical as there
+LINES_CLASSES: List[str] = sorted(
+    [f"{box} rect. {side} {part}" for box in ("Big", "Small") for side in ("left", "right") for part in ("bottom", "main", "top")]
+    + ["Circle central", "Circle left", "Circle right", "Goal left crossbar", "Goal left post left ", "Goal left post right",
+       "Goal right crossbar", "Goal right post left", "Goal right post right", "Goal unknown", "Line unknown", "Middle line",
+       "Side line bottom", "Side line left", "Side line right", "Side line top"])
+
+
+def symmetric_class(name: str) -> str:
+    """The class a line maps to under the point reflection through the pitch centre
+    (SoccerPitch.symetric_classes, soccerpitch.py:46-75): left <-> right everywhere, top <-> bottom for the
+    rectangle and side lines; the goal posts keep their own 'left' / 'right'."""
+    flip = {"top": "bottom", "bottom": "top", "left": "right", "right": "left", "main": "main"}
+    if name in ("Middle line", "Circle central", "Goal unknown", "Line unknown"):
+        return name
+    if name.startswith("Goal "):
+        side, rest = name.rstrip()[5:].split(" ", 1)
+        out = f"Goal {flip[side]} {rest}"
+        return out + " " if out == "Goal left post left" else out      # the dataset's own spelling
+    if name.startswith("Circle "):
+        return "Circle " + flip[name[7:]]
+    if name.startswith("Side line "):
+        return "Side line " + flip[name[10:]]
+    box, _, side, part = name.split(" ")           # '<Big|Small> rect. <side> <part>'
+    return f"{box} rect. {flip[side]} {flip[part]}"
+
+
+def line_extremities() -> Dict[str, Tuple[str, str]]:
+    """class -> names of its two end points, in the reference's insertion order
+    (SoccerPitch.line_extremities_keys, soccerpitch.py:318-375); the order fixes the sampling direction."""
+    ext: Dict[str, Tuple[str, str]] = {}
+    for box, tag in (("Big", "PENALTY_AREA"), ("Small", "GOAL_AREA")):
+        for side, s in (("left", "L"), ("right", "R")):
+            ext[f"{box} rect. {side} bottom"] = (f"{s}_{tag}_BL_CORNER", f"{s}_{tag}_BR_CORNER")
+            ext[f"{box} rect. {side} top"] = (f"{s}_{tag}_TL_CORNER", f"{s}_{tag}_TR_CORNER")
+            ext[f"{box} rect. {side} main"] = ((f"{s}_{tag}_TR_CORNER", f"{s}_{tag}_BR_CORNER") if side == "left"
+                                               else (f"{s}_{tag}_TL_CORNER", f"{s}_{tag}_BL_CORNER"))
+    ext["Side line top"] = ("TL_PITCH_CORNER", "TR_PITCH_CORNER")
+    ext["Side line bottom"] = ("BL_PITCH_CORNER", "BR_PITCH_CORNER")
+    ext["Side line left"] = ("TL_PITCH_CORNER", "BL_PITCH_CORNER")
+    ext["Side line right"] = ("TR_PITCH_CORNER", "BR_PITCH_CORNER")
+    ext["Middle line"] = ("T_TOUCH_AND_HALFWAY_LINES_INTERSECTION", "B_TOUCH_AND_HALFWAY_LINES_INTERSECTION")
+    ext["Goal left crossbar"] = ("L_GOAL_TR_POST", "L_GOAL_TL_POST")
+    ext["Goal left post left "] = ("L_GOAL_TL_POST", "L_GOAL_BL_POST")
+    ext["Goal left post right"] = ("L_GOAL_TR_POST", "L_GOAL_BR_POST")
+    ext["Goal right crossbar"] = ("R_GOAL_TL_POST", "R_GOAL_TR_POST")
+    ext["Goal right post left"] = ("R_GOAL_TL_POST", "R_GOAL_BL_POST")
+    ext["Goal right post right"] = ("R_GOAL_TR_POST", "R_GOAL_BR_POST")
+    ext["Circle right"] = ("TR_16M_LINE_AND_PENALTY_ARC_INTERSECTION", "BR_16M_LINE_AND_PENALTY_ARC_INTERSECTION")
+    ext["Circle left"] = ("TL_16M_LINE_AND_PENALTY_ARC_INTERSECTION", "BL_16M_LINE_AND_PENALTY_ARC_INTERSECTION")
+    return ext
+
+
+def sample_field_points(dist: float = 0.1, dist_circles: float = 0.2) -> Dict[str, np.ndarray]:
+    """class -> (n, 3) points sampled along the pitch element (SoccerPitch.sample_field_points,
+    soccerpitch.py:420-510): the centre circle every ``dist_circles`` metres of arc from angle 0, the two
+    penalty arcs between their 16 m-line marks (bottom -> top on the right, top -> bottom on the left, end
+    point appended), straight lines every ``dist`` metres from the first extremity (running sum, end
+    point appended)."""
+    P = get_pitch()
+    r = CENTER_CIRCLE_RADIUS
+    out: Dict[str, np.ndarray] = {}
+
+    def arc(center, a0, a1, closed):
+        if a1 < a0:
+            a1 += 2 * np.pi
+        n = int(r * (a1 - a0) / dist_circles)
+        da = dist_circles / r
+        pts = [np.array((center[0] + np.cos(a0) * r, center[1] + np.sin(a0) * r, 0.0))]
+        for i in range(1, n if closed else n + 1):
+            a = a0 + i * da
+            pts.append(np.array((center[0] + np.cos(a) * r, center[1] + np.sin(a) * r, 0)))
+        if not closed:
+            pts.append(np.array((center[0] + np.cos(a1) * r, center[1] + np.sin(a1) * r, 0.0)))
+        return np.array(pts, dtype=np.float64)
+
+    out["Circle central"] = arc(P["CENTER_MARK"], 0.0, 2 * np.pi, True)
+    for key, (na, nb) in line_extremities().items():
+        a, b = np.asarray(P[na], dtype=np.float64), np.asarray(P[nb], dtype=np.float64)
+        if key.startswith("Circle"):
+            c = np.asarray(P["R_PENALTY_MARK" if key == "Circle right" else "L_PENALTY_MARK"], dtype=np.float64)
+            ang = lambda q: np.arctan2(q[1] - c[1], q[0] - c[0]) + 2 * np.pi
+            a0, a1 = (ang(b), ang(a)) if key == "Circle right" else (ang(a), ang(b))
+            out[key] = arc(c, a0, a1, False)
+        else:
+            total = np.sqrt(np.sum(np.square(a - b)))
+            n = int(total / dist - 1)
+            v = b - a
+            v = v / np.linalg.norm(v)
+            pts, prev = [a], a
+            for _ in range(n):
+                prev = prev + dist * v
+                pts.append(prev)
+            pts.append(b)
+            out[key] = np.array(pts, dtype=np.float64)
+    return out

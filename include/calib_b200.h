@@ -108,6 +108,11 @@ int cal_conv2d(const CalConvArgs* h_args, void* stream);
  * w: fp32 (64, 27) BN folded [co][ci*9+ky*3+kx]; y: fp16 NHWC (B,Ho,Wo,64). */
 int cal_stem_conv(const float* x, const float* w, const float* bias, void* y,
                   int B, int H, int W, int Ho, int Wo, void* stream);
+/* The same from the frame as cv2.imread leaves it: x (B,H,W,3) uint8 HWC BGR; T.ToTensor's float32
+ * division by 255 (src/models/hrnet/transforms.py:59-68, src/utils/make_submit.py:66) is folded into the
+ * load - bit-identical to cal_stem_conv on ToTensor's output, a quarter of the host->device bytes. */
+int cal_stem_conv_u8(const uint8_t* x, const float* w, const float* bias, void* y,
+                     int B, int H, int W, int Ho, int Wo, void* stream);
 
 #define CAL_MAX_SOURCES 6
 typedef struct CalCombineArgs {

@@ -12,7 +12,7 @@ CAL_MAX_SOURCES = 6
 
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
-    "cal_stem_conv", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
+    "cal_stem_conv", "cal_stem_conv_u8", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points", "cal_evaluate_cameras",
     "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",
 ]
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.cal_line_decode.argtypes = [vp, i32, i32, i32, i32, f64, f32, vp, vp]
     L.cal_conv2d.argtypes = [C.POINTER(ConvArgs), vp]
     L.cal_stem_conv.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.cal_stem_conv_u8.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]
     L.cal_head_fused.argtypes = [C.POINTER(HeadArgs), vp]
     L.cal_debug_tma_probe.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]

@@ -24,7 +24,10 @@ constexpr int STEM_K = 27;
 // (Four pixels per thread need 215 registers and measured slower: 2.8 vs 1.9 ms per step.)
 constexpr int STEM_THREADS = 256;
 
-__global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const float* __restrict__ x,
+// U8: the frame as cv2.imread leaves it - uint8 HWC BGR - with ToTensor's float32 division by 255
+// (transforms.py:59-68, make_submit.py:66) folded into the load: a quarter of the host->device bytes.
+template <bool U8>
+__global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const void* __restrict__ xin,
                                                                  const float* __restrict__ w,
                                                                  const float* __restrict__ bias,
                                                                  __half* __restrict__ y, int B, int H, int W,
@@ -47,9 +50,8 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const float* __
   const bool two = ox + 1 < Wo;
   // input columns 2*ox-1 .. 2*ox+3 (the two pixels share column 2*ox+1), rows 2*oy-1 .. 2*oy+1
   float in[3][3][5];
-#pragma unroll
-  for (int ci = 0; ci < 3; ++ci) {
-    const float* plane = x + (static_cast<size_t>(b) * 3 + ci) * H * W;
+  if (U8) {
+    const uint8_t* img = static_cast<const uint8_t*>(xin) + static_cast<size_t>(b) * H * W * 3;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = 2 * oy + ky - 1;
@@ -57,7 +59,25 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const float* __
       for (int kx = 0; kx < 5; ++kx) {
         const int ix = 2 * ox + kx - 1;
         const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
-        in[ci][ky][kx] = ok ? __ldg(plane + static_cast<size_t>(iy) * W + ix) : 0.0f;
+        const uint8_t* px = img + (static_cast<size_t>(iy) * W + ix) * 3;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) in[ci][ky][kx] = ok ? __fdiv_rn(static_cast<float>(__ldg(px + ci)), 255.0f) : 0.0f;
+      }
+    }
+  } else {
+    const float* x = static_cast<const float*>(xin);
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+      const float* plane = x + (static_cast<size_t>(b) * 3 + ci) * H * W;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = 2 * oy + ky - 1;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          const int ix = 2 * ox + kx - 1;
+          const bool ok = (iy >= 0) && (iy < H) && (ix >= 0) && (ix < W);
+          in[ci][ky][kx] = ok ? __ldg(plane + static_cast<size_t>(iy) * W + ix) : 0.0f;
+        }
       }
     }
   }
@@ -216,8 +236,8 @@ __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineP
 }  // namespace
 }  // namespace cal
 
-extern "C" int cal_stem_conv(const float* x, const float* w, const float* bias, void* y, int B,
-                             int H, int W, int Ho, int Wo, void* stream) {
+static int stem_launch(const void* x, bool u8, const float* w, const float* bias, void* y, int B, int H, int W, int Ho, int Wo,
+                       void* stream) {
   using namespace cal;
   CAL_REQUIRE(x && w && bias && y, CAL_E_INVALID, "cal_stem_conv: null pointer");
   CAL_REQUIRE(B >= 1 && H >= 1 && W >= 1 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, CAL_E_INVALID,
@@ -226,10 +246,24 @@ extern "C" int cal_stem_conv(const float* x, const float* w, const float* bias, 
   const int threads = STEM_THREADS;
   const long long blocks = (total + threads - 1) / threads;
   CAL_REQUIRE(blocks < (1ll << 31), CAL_E_UNSUPPORTED, "cal_stem_conv: too many pixels");
-  stem_conv_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, w, bias, reinterpret_cast<__half*>(y), B, H, W, Ho, Wo);
+  if (u8)
+    stem_conv_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, reinterpret_cast<__half*>(y), B, H, W, Ho, Wo);
+  else
+    stem_conv_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, reinterpret_cast<__half*>(y), B, H, W, Ho, Wo);
   CAL_CHECK_CUDA(cudaGetLastError());
   return CAL_OK;
+}
+
+extern "C" int cal_stem_conv(const float* x, const float* w, const float* bias, void* y, int B,
+                             int H, int W, int Ho, int Wo, void* stream) {
+  return stem_launch(x, false, w, bias, y, B, H, W, Ho, Wo, stream);
+}
+
+extern "C" int cal_stem_conv_u8(const uint8_t* x, const float* w, const float* bias, void* y, int B,
+                                int H, int W, int Ho, int Wo, void* stream) {
+  return stem_launch(x, true, w, bias, y, B, H, W, Ho, Wo, stream);
 }
 
 extern "C" int cal_fuse_combine(const CalCombineArgs* a, void* stream) {

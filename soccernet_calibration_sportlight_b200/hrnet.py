@@ -500,9 +500,17 @@ class HRNetHeatmap:
             raise RuntimeError("call .to('cuda:N') first")
         if x.device != self.device:
             x = x.to(self.device, non_blocking=True)
-        x = x.contiguous().float()
+        # (B,3,H,W) float in [0,1] (the reference's input), or (B,H,W,3) uint8 BGR frames as cv2.imread leaves
+        # them: ToTensor's /255 then happens inside the stem kernel
+        if x.dtype == torch.uint8:
+            if x.dim() != 4 or x.shape[-1] != 3:
+                raise ValueError("uint8 frames must be (B,H,W,3) BGR")
+            x = x.contiguous()
+            B, H, W, _ = x.shape
+        else:
+            x = x.contiguous().float()
+            B, _, H, W = x.shape
         net = self.net
-        B, _, H, W = x.shape
         with torch.cuda.device(self.device):
             Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
             stem = torch.empty((B, Ho, Wo, 64), dtype=torch.float16, device=self.device)

@@ -131,13 +131,18 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
 
 
 def stem_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """x fp32 NCHW (B,3,H,W); w fp32 (64,27); y fp16 NHWC (B,Ho,Wo,64)."""
-    B, _, H, W = x.shape
+    """x fp32 NCHW (B,3,H,W) in [0,1], or uint8 NHWC (B,H,W,3) as cv2.imread leaves it (ToTensor's /255 folded
+    into the load); w fp32 (64,27); y fp16 NHWC (B,Ho,Wo,64)."""
+    u8 = x.dtype == torch.uint8
+    if u8:
+        B, H, W, _ = x.shape
+    else:
+        B, _, H, W = x.shape
     _, Ho, Wo, _ = y.shape
     with _Launch("stem_conv", x.device):
-        st = _lib.lib().cal_stem_conv(_dev(x, torch.float32, "stem x"), _dev(w, torch.float32, "stem w"),
-                                      _dev(bias, torch.float32, "stem bias"), _dev(y, torch.float16, "stem y"),
-                                      B, H, W, Ho, Wo, _stream())
+        fn = _lib.lib().cal_stem_conv_u8 if u8 else _lib.lib().cal_stem_conv
+        st = fn(_dev(x, torch.uint8 if u8 else torch.float32, "stem x"), _dev(w, torch.float32, "stem w"),
+                _dev(bias, torch.float32, "stem bias"), _dev(y, torch.float16, "stem y"), B, H, W, Ho, Wo, _stream())
     _lib.check(st, "cal_stem_conv")
     return y
 

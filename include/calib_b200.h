@@ -162,6 +162,41 @@ typedef struct CalHeadArgs {
  * cal_fuse_combine + cal_conv2d). */
 int cal_head_fused(const CalHeadArgs* h_args, void* stream);
 
+/* ------------------------------------------------------------------ engine -- */
+/* The whole network behind one call: what `HRNetHeatmap(hrnet_config).forward(x)` is in the reference
+ * (src/models/hrnet/model.py:130-150 -> HighResolutionNet.__init__/forward, src/models/hrnet/hrnet.py:255-330,
+ * 437-511; src/models/line/hrnet.py:30-249), for a host written in any language.  The library walks the
+ * architecture, folds eval-mode BatchNorm, packs the weights (cal_hrnet_create) and owns the layer schedule
+ * (cal_hrnet_forward: one launch per fused conv, intermediate tensors from the CUDA stream-ordered
+ * allocator - the one exception to "nothing is allocated behind the ABI").  The fields mirror the reference's
+ * model_config/hrnet_*.yaml. */
+typedef struct CalHrnetStage {
+  int32_t num_modules, num_branches;
+  int32_t block_type;            /* 0 = BASIC, 1 = BOTTLENECK */
+  int32_t num_blocks[4], num_channels[4];
+} CalHrnetStage;
+
+typedef struct CalHrnetConfig {
+  int32_t kind;                  /* 0 = keypoint net (stem skip, `upscale`, LogSoftmax); 1 = line net (Softmax) */
+  int32_t num_classes;           /* 58 / 23 (<= 64) */
+  int32_t stem_width;            /* 64 */
+  int32_t upscale;               /* keypoint net: head resolution / first-branch resolution (2, or 4 for w48x4) */
+  CalHrnetStage stage[4];        /* stage1 .. stage4 */
+} CalHrnetConfig;
+
+/* Number of floats of the weight blob: every tensor of the reference's `nn_state_dict` in its own order
+ * (conv weight, [conv bias], BN weight, bias, running_mean, running_var; `num_batches_tracked` skipped),
+ * each flattened row-major, concatenated. */
+int cal_hrnet_weight_count(const CalHrnetConfig* h_cfg, size_t* h_n_floats);
+int cal_hrnet_create(const CalHrnetConfig* h_cfg, const float* h_weights, size_t n_floats, void** h_handle);
+/* x: (B,3,H,W) fp32 NCHW in [0,1] BGR (x_is_u8 = 0: the reference's input) or (B,H,W,3) uint8 HWC BGR frames as
+ * cv2.imread leaves them (x_is_u8 = 1); heat: (B, num_classes, h, w) fp32 NCHW, (h, w) from cal_hrnet_output_shape:
+ * log-probabilities (keypoints, H/2 x W/2) or probabilities (lines, H/4 x W/4). */
+int cal_hrnet_forward(void* handle, const void* x, int x_is_u8, int B, int H, int W, float* heat, void* stream);
+int cal_hrnet_output_shape(void* handle, int H, int W, int* h_n_classes, int* h_h, int* h_w);
+long cal_hrnet_launches(void* handle);    /* kernels launched through this handle so far */
+int cal_hrnet_destroy(void* handle);
+
 /* ------------------------------------------------------------ camera solve -- */
 
 #define CAL_NUM_KEYPOINTS 57

@@ -13,7 +13,8 @@ CAL_MAX_SOURCES = 6
 EXPORTS = [
     "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
     "cal_stem_conv", "cal_stem_conv_u8", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
-    "cal_line_points", "cal_evaluate_cameras",
+    "cal_line_points", "cal_evaluate_cameras", "cal_hrnet_weight_count", "cal_hrnet_create", "cal_hrnet_forward",
+    "cal_hrnet_output_shape", "cal_hrnet_launches", "cal_hrnet_destroy",
     "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",
 ]
 
@@ -49,6 +50,16 @@ class HeadArgs(C.Structure):
                 ("Cout_pad", C.c_int32), ("Cout_rows", C.c_int32),
                 ("w2", C.c_void_p), ("bias2", C.c_void_p), ("heat", C.c_void_p),
                 ("n_classes", C.c_int32), ("mode", C.c_int32)]
+
+
+class HrnetStage(C.Structure):
+    _fields_ = [("num_modules", C.c_int32), ("num_branches", C.c_int32), ("block_type", C.c_int32),
+                ("num_blocks", C.c_int32 * 4), ("num_channels", C.c_int32 * 4)]
+
+
+class HrnetConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("num_classes", C.c_int32), ("stem_width", C.c_int32), ("upscale", C.c_int32),
+                ("stage", HrnetStage * 4)]
 
 
 class SolveParams(C.Structure):
@@ -98,10 +109,17 @@ def lib() -> C.CDLL:
     L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
     L.cal_line_points.argtypes = [vp, i32, i32, vp, vp, f32, vp, vp]
+    L.cal_hrnet_weight_count.argtypes = [C.POINTER(HrnetConfig), C.POINTER(C.c_size_t)]
+    L.cal_hrnet_create.argtypes = [C.POINTER(HrnetConfig), vp, C.c_size_t, C.POINTER(vp)]
+    L.cal_hrnet_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp]
+    L.cal_hrnet_output_shape.argtypes = [vp, i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.cal_hrnet_launches.argtypes = [vp]
+    L.cal_hrnet_destroy.argtypes = [vp]
     L.cal_evaluate_cameras.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, i32, i32, f64, vp, vp, i32, i32, vp, vp, vp]
     for name in EXPORTS:
         if hasattr(L, name) and name != "cal_last_error":
             getattr(L, name).restype = C.c_int
+    L.cal_hrnet_launches.restype = C.c_long
     _lib = L
     return L
 

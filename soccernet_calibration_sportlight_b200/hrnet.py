@@ -331,6 +331,11 @@ class HRNetHeatmap:
         self.slice_major = os.environ.get("CAL_W_SLICES", "1") != "0"
         self.branch_streams = os.environ.get("CAL_BRANCH_STREAMS", "0") != "0"   # measured neutral: off
         self._streams: List[torch.cuda.Stream] = []
+        # the forward through the library's own engine (csrc/engine.cu: cal_hrnet_create / cal_hrnet_forward),
+        # one C call per network instead of ~300 ctypes calls; CAL_ENGINE=0 walks the schedule here, op by op
+        # (the readable twin: same kernels, same order, bit-identical output - and the per-launch profile)
+        self.use_engine = os.environ.get("CAL_ENGINE", "1") != "0"
+        self._engine = None
 
     # -- nn.Module-like surface used by the reference's callers
     def eval(self):
@@ -343,6 +348,7 @@ class HRNetHeatmap:
         return self._sd
 
     def load_state_dict(self, sd, strict: bool = True):
+        self._engine_release()
         schema = state_dict_schema(self.cfg, self.kind)
         sd = {k.replace("_orig_mod.", ""): v for k, v in sd.items()}  # metamodel.py:113-117
         missing = [k for k in schema if k not in sd]
@@ -361,7 +367,74 @@ class HRNetHeatmap:
             raise RuntimeError("HRNetHeatmap runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.device = device
         self._pack()
+        self._engine_release()
         return self
+
+    # -- the C-ABI engine
+    def engine_config(self) -> "ops._lib.HrnetConfig":
+        """The CalHrnetConfig of this architecture (include/calib_b200.h)."""
+        c = ops._lib.HrnetConfig()
+        c.kind = 0 if self.kind == "keypoints" else 1
+        c.num_classes, c.stem_width = self.num_classes, int(self.cfg["stem_width"])
+        c.upscale = int(self.net["upscale"])
+        for i in range(4):
+            st = self.cfg[f"stage{i + 1}"]
+            c.stage[i].num_modules, c.stage[i].num_branches = int(st["num_modules"]), int(st["num_branches"])
+            c.stage[i].block_type = 1 if st["block_type"] == "BOTTLENECK" else 0
+            for b in range(int(st["num_branches"])):
+                c.stage[i].num_blocks[b], c.stage[i].num_channels[b] = int(st["num_blocks"][b]), int(st["num_channels"][b])
+        return c
+
+    def weight_blob(self) -> torch.Tensor:
+        """Every float tensor of the state_dict in its own order, flattened and concatenated
+        (num_batches_tracked skipped): cal_hrnet_create's input."""
+        sd = self.state_dict()
+        return torch.cat([sd[k].detach().reshape(-1).float() for k in state_dict_schema(self.cfg, self.kind)
+                          if not k.endswith("num_batches_tracked")]).contiguous()
+
+    def _engine_handle(self):
+        if self._engine is None:
+            import ctypes as C
+            blob = self.weight_blob()
+            h = C.c_void_p()
+            cfg = self.engine_config()
+            with torch.cuda.device(self.device):
+                st = ops._lib.lib().cal_hrnet_create(C.byref(cfg), blob.data_ptr(), blob.numel(), C.byref(h))
+            ops._lib.check(st, "cal_hrnet_create")
+            self._engine = h
+            self._engine_launches = 0
+        return self._engine
+
+    def _engine_release(self):
+        if self._engine is not None:
+            ops._lib.lib().cal_hrnet_destroy(self._engine)
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self._engine_release()
+        except Exception:       # noqa: BLE001 - interpreter shutdown
+            pass
+
+    def _engine_forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        import ctypes as C
+        h = self._engine_handle()
+        u8 = x.dtype == torch.uint8
+        if u8:
+            B, H, W, _ = x.shape
+        else:
+            B, _, H, W = x.shape
+        L = ops._lib.lib()
+        nc, oh, ow = C.c_int32(), C.c_int32(), C.c_int32()
+        ops._lib.check(L.cal_hrnet_output_shape(h, H, W, C.byref(nc), C.byref(oh), C.byref(ow)), "cal_hrnet_output_shape")
+        heat = torch.empty((B, nc.value, oh.value, ow.value), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = L.cal_hrnet_forward(h, x.data_ptr(), int(u8), B, H, W, heat.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        ops._lib.check(st, "cal_hrnet_forward")
+        n = int(L.cal_hrnet_launches(h))
+        ops.LAUNCHES += n - self._engine_launches
+        self._engine_launches = n
+        return [heat]
 
     def cuda(self, idx: int = 0):
         return self.to(f"cuda:{idx}")
@@ -510,6 +583,9 @@ class HRNetHeatmap:
         else:
             x = x.contiguous().float()
             B, _, H, W = x.shape
+        if self.use_engine and ops.PROFILE is None and not self.branch_streams and self.fused_head and self.chained_head \
+                and self.slice_major:
+            return self._engine_forward(x)
         net = self.net
         with torch.cuda.device(self.device):
             Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1

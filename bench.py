@@ -201,7 +201,10 @@ def run_b200(args, rank, world, local_rank):
 
     g = torch.Generator().manual_seed(1234 + rank)
     nh, nw = args.net_hw
-    host = torch.randint(0, 256, (B, 3, nh, nw), generator=g, dtype=torch.uint8).float().div_(255.0).pin_memory()
+    # frames as cv2.imread leaves them (make_submit.py:66): uint8 HWC BGR; ToTensor's /255 runs in the stem kernel
+    # (--float-frames: the reference's float CHW tensor instead, four times the bytes)
+    u8 = torch.randint(0, 256, (B, nh, nw, 3), generator=g, dtype=torch.uint8)
+    host = (u8.permute(0, 3, 1, 2).float().div_(255.0).contiguous() if args.float_frames else u8).pin_memory()
     frames = host.to(dev)
     synth = None
     if solve:
@@ -304,7 +307,8 @@ def run_b200(args, rank, world, local_rank):
             same = [True] * len(mine)
             for r in range(world):
                 gr = torch.Generator().manual_seed(1234 + r)
-                fr = torch.randint(0, 256, (B, 3, nh, nw), generator=gr, dtype=torch.uint8).float().div_(255.0).to(dev)
+                fr = torch.randint(0, 256, (B, nh, nw, 3), generator=gr, dtype=torch.uint8)
+                fr = (fr.permute(0, 3, 1, 2).float().div_(255.0).contiguous() if args.float_frames else fr).to(dev)
                 sy = torch.from_numpy(synthetic_keypoints(B, seed=100 + r)).to(dev) if solve else None
                 o = pipe(fr, keypoints_override=sy) if solve else pipe(fr)
                 alone = [o["keypoints"]] + ([o["cameras"]] if solve else [])
@@ -377,10 +381,13 @@ def run_b200(args, rank, world, local_rank):
                        "BASELINE config 2", "BASELINE config 5 sweep").replace("BASELINE config 3", "BASELINE config 5 sweep"),
                    "name": args.workload, "batch_per_gpu": B, "global_batch": world * B,
                    "resolution": [nw, nh], "weights": "random-init HRNet-w48 (seeded)",
+                   "frames": ("float32 CHW in [0,1] (the reference's ToTensor output)" if args.float_frames else
+                              "uint8 HWC BGR (cv2.imread layout), /255 folded into the stem kernel"),
+                   "forward": "cal_hrnet_forward (C++ engine)" if os.environ.get("CAL_ENGINE", "1") != "0" else "hrnet.py schedule",
                    "camera_solve_inputs": ("synthetic keypoints of plausible cameras (keypoints_override): random-init weights "
                                            "give conf ~ 1/58 < every threshold; the networks' own decoded keypoints are still "
                                            "produced every step") if solve else None,
-                   "l2": "inputs larger than L2 (398 MB of frames + GBs of activations per step)",
+                   "l2": "working set larger than L2 (100 MB of uint8 frames + GBs of activations per step)",
                    "camera_solve_schedule": (("second stream, under the next batch's networks (co-resident blocks, "
                                               f"{pipe.solve_headroom} B shared-memory headroom)") if pipe.overlap_solve
                                              else "same stream, after the networks") if solve else None,
@@ -426,6 +433,7 @@ def main():
     ap.add_argument("--width", type=int, default=W_IMG)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--float-frames", action="store_true", help="feed float32 CHW frames (398 MB per batch) instead of uint8 HWC")
     ap.add_argument("--shapes-out", default="", help="write per-(kernel, shape) device times of one profiled step")
     args = ap.parse_args()
     # the network runs at --height x --width; keypoints stay in 960x540 coordinates (the camera

@@ -198,7 +198,9 @@ static int pack(Net& n, Conv& c, const double* w, int cout, int cin, int cin_str
   for (int o = 0; o < cout; ++o)
     for (int ci = 0; ci < cin; ++ci)
       for (int t = 0; t < kk; ++t)
-        wk[((size_t)o * kk + t) * c.cin_pad + ci] = __double2half(w[((size_t)o * cin_stride + cin_off + ci) * kk + t]);
+        // double -> float -> half, the two roundings torch's .to(torch.float16) performs on a float64 tensor (the
+        // Python packer, packing.pack_conv): the engine and its twin must produce the same bits
+        wk[((size_t)o * kk + t) * c.cin_pad + ci] = __float2half((float)w[((size_t)o * cin_stride + cin_off + ci) * kk + t]);
   std::vector<float> bp(c.cout_pad, 0.0f);
   for (int o = 0; o < cout; ++o) bp[o] = (float)b[o];
   int rc = to_device(n, bp, &c.b);

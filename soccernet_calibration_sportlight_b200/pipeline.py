@@ -74,7 +74,9 @@ class CalibrationPipeline:
     @torch.no_grad()
     def __call__(self, frames: torch.Tensor, keypoints_override: Optional[torch.Tensor] = None,
                  defer_solve: bool = False) -> Dict[str, torch.Tensor]:
-        """frames: (B,3,H,W) fp32 in [0,1] BGR, on the host (pinned) or on the device.
+        """frames: (B,3,H,W) fp32 in [0,1] BGR (the reference's tensor), or (B,H,W,3) uint8 BGR as cv2.imread leaves
+        them (ToTensor's /255 then happens in the stem kernel: a quarter of the bytes to move), on the host
+        (pinned) or on the device.
         Returns device tensors: 'keypoints' (B,57,3), optionally 'lines' (B,23,2,3), and
         'cameras' (B,16) fp64 records (see prediction.CameraCreator.batch_records).
         ``keypoints_override`` (B,57,3) feeds the camera solve instead of the network's own
@@ -86,9 +88,10 @@ class CalibrationPipeline:
         line_pts = None
         if self.line_model is not None:
             # line heat maps are a quarter of the network input: peaks -> `size` coordinates
-            sy, sx = self.size[0] / x.shape[-2], self.size[1] / x.shape[-1]
+            in_h, in_w = (x.shape[1], x.shape[2]) if x.dtype == torch.uint8 else (x.shape[-2], x.shape[-1])
+            sy, sx = self.size[0] / in_h, self.size[1] / in_w
             if abs(sx - sy) > 1e-3 * sx:
-                raise ValueError(f"network input {tuple(x.shape[-2:])} and size {self.size} differ in aspect ratio")
+                raise ValueError(f"network input {(in_h, in_w)} and size {self.size} differ in aspect ratio")
             self.line_model.prediction_transform.scale = 4.0 * sx
         if self.line_model is not None and self.two_streams:
             # the two networks are independent: on two streams the ramp-up / tail of every

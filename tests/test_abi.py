@@ -102,7 +102,7 @@ def test_forward_through_the_c_abi_alone():
         nc, oh, ow = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         assert L.cal_hrnet_output_shape(h, 96, 160, ctypes.byref(nc), ctypes.byref(oh), ctypes.byref(ow)) == 0
         heat = torch.empty((2, nc.value, oh.value, ow.value), device="cuda:0")
-        xd = x.cuda()
+        xd = x.contiguous().cuda()
         st = torch.cuda.current_stream().cuda_stream
         assert L.cal_hrnet_forward(h, xd.data_ptr(), 0, 2, 96, 160, heat.data_ptr(), st) == 0, L.cal_last_error()
         with torch.no_grad():

@@ -325,9 +325,17 @@ CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, 
     }
     T.sync();
   } else if (n >= 6 && n <= NKP) {
+    // Samples that draw the same five points (in any order) give the same pose up to rounding: each
+    // distinct point set is evaluated once (with 6..8 matches there are only 6..56 of them, one round of the
+    // team instead of two), every iteration of OpenCV's loop then looks its result up.
+    unsigned char* rep = samples + 500;            // iteration -> first iteration with the same point set
+    unsigned char* todo = samples + 600;           // the representatives evaluated in this round
     if (T.tid == 0) {
       cvx::CvRng rng(0xFFFFFFFFFFFFFFFFull);
-      for (int h = 0; h < 100; ++h)
+      unsigned long long* smask = reinterpret_cast<unsigned long long*>(ws.part);     // scratch: 100 point-set masks
+      unsigned long long* smask2 = reinterpret_cast<unsigned long long*>(ws.JtJ);
+      for (int h = 0; h < 100; ++h) {
+        unsigned long long m = 0;
         for (int i = 0; i < 5; ++i) {
           int v;
           for (;;) {
@@ -337,15 +345,41 @@ CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, 
             if (!dup) break;
           }
           samples[h * 5 + i] = (unsigned char)v;
+          m |= 1ull << v;
         }
+        (h < MAXOBS ? smask[h] : smask2[h - MAXOBS]) = m;
+        int r = h;
+        for (int q = 0; q < h; ++q)
+          if ((q < MAXOBS ? smask[q] : smask2[q - MAXOBS]) == m) { r = q; break; }
+        rep[h] = (unsigned char)r;
+        ws.hyp_cnt[h] = -2;                        // not evaluated yet
+      }
+      ws.hn = 0;                                   // scratch: next iteration of OpenCV's loop to account for
     }
     T.sync();
-    for (int base = 0; base < 100; base += T.nt) {
-      const int budget = ws.pnp_niters;
+    for (;;) {
+      if (T.tid == 0) {
+        const int pos = ws.hn;
+        int ntodo = 0, end = pos;
+        if (pos >= ws.pnp_niters || pos >= 100) {
+          ntodo = -1;
+        } else {
+          for (; end < 100 && end < ws.pnp_niters; ++end) {
+            const int r = rep[end];
+            if (ws.hyp_cnt[r] != -2) continue;     // evaluated in an earlier round (or queued in this one: -3)
+            if (ntodo == T.nt || ntodo == 64) break;
+            todo[ntodo++] = (unsigned char)r;
+            ws.hyp_cnt[r] = -3;
+          }
+        }
+        ws.iters = ntodo; ws.flag = end;
+      }
       T.sync();
-      if (base >= budget) break;
-      const int h = base + T.tid;
-      if (h < 100 && h < budget) {
+      const int ntodo = ws.iters, end = ws.flag;
+      T.sync();
+      if (ntodo < 0) break;
+      if (T.tid < ntodo) {
+        const int h = todo[T.tid];
         double obj[15], xn[10], R[9], t[3];
         for (int i = 0; i < 5; ++i) {
           const int k = samples[h * 5 + i];
@@ -363,13 +397,16 @@ CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, 
       }
       T.sync();
       if (T.tid == 0) {
-        for (int q = base; q < base + T.nt && q < 100 && q < ws.pnp_niters; ++q) {
-          const int good = ws.hyp_cnt[q];
+        int q = ws.hn;
+        for (; q < end && q < ws.pnp_niters; ++q) {
+          const int r = rep[q];
+          const int good = ws.hyp_cnt[r];
           if (good > (ws.pnp_maxgood > 4 ? ws.pnp_maxgood : 4)) {
-            ws.pnp_best = q; ws.pnp_maxgood = good;
+            ws.pnp_best = r; ws.pnp_maxgood = good;
             ws.pnp_niters = cvx::update_num_iters(0.99, (double)(n - good) / n, 5, ws.pnp_niters);
           }
         }
+        ws.hn = end;
       }
       T.sync();
     }

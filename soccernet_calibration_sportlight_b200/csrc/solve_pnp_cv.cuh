@@ -66,6 +66,7 @@ CAL_HD_NOINLINE inline void jacobi_svd(double* At, int astep, double* W, double*
         double* Ai = At + i * astep;
         double* Aj = At + j * astep;
         double a = W[i], p = 0, b = W[j];
+        if (a == 0 || b == 0) continue;      // an all-zero row: p = 0 <= eps * sqrt(a * b) = 0, the pair is never rotated
         for (int k = 0; k < m; ++k) p += Ai[k] * Aj[k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
         p *= 2;

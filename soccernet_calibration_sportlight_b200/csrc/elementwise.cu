@@ -84,37 +84,38 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const void* __r
   __half* out = y + ((static_cast<size_t>(b) * Ho + oy) * Wo + ox) * STEM_CO;
 #pragma unroll
   for (int c0 = 0; c0 < STEM_CO; c0 += 16) {
-    // adjacent channel pairs in packed fp32x2 FMAs (sm_100 FFMA2: two IEEE fmaf per instruction, the weight pair
-    // comes straight out of the 128-bit shared-memory read): half the FMA issue slots, bit-identical results
-    float2 acc0[8], acc1[8];
+    float acc0[16], acc1[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc0[j] = make_float2(s_b[c0 + 2 * j], s_b[c0 + 2 * j + 1]); acc1[j] = acc0[j]; }
+    for (int j = 0; j < 16; ++j) { acc0[j] = s_b[c0 + j]; acc1[j] = acc0[j]; }
 #pragma unroll
     for (int k = 0; k < STEM_K; ++k) {
       const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
-      const float2 v0 = make_float2(in[ci][ky][kx], in[ci][ky][kx]), v1 = make_float2(in[ci][ky][kx + 2], in[ci][ky][kx + 2]);
+      const float v0 = in[ci][ky][kx], v1 = in[ci][ky][kx + 2];
       const float4* wr = reinterpret_cast<const float4*>(s_w + k * STEM_CO + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 ww = wr[q];
-        const float2 wa = make_float2(ww.x, ww.y), wb = make_float2(ww.z, ww.w);
-        acc0[2 * q + 0] = __ffma2_rn(v0, wa, acc0[2 * q + 0]);
-        acc0[2 * q + 1] = __ffma2_rn(v0, wb, acc0[2 * q + 1]);
-        acc1[2 * q + 0] = __ffma2_rn(v1, wa, acc1[2 * q + 0]);
-        acc1[2 * q + 1] = __ffma2_rn(v1, wb, acc1[2 * q + 1]);
+        acc0[4 * q + 0] = fmaf(v0, ww.x, acc0[4 * q + 0]);
+        acc0[4 * q + 1] = fmaf(v0, ww.y, acc0[4 * q + 1]);
+        acc0[4 * q + 2] = fmaf(v0, ww.z, acc0[4 * q + 2]);
+        acc0[4 * q + 3] = fmaf(v0, ww.w, acc0[4 * q + 3]);
+        acc1[4 * q + 0] = fmaf(v1, ww.x, acc1[4 * q + 0]);
+        acc1[4 * q + 1] = fmaf(v1, ww.y, acc1[4 * q + 1]);
+        acc1[4 * q + 2] = fmaf(v1, ww.z, acc1[4 * q + 2]);
+        acc1[4 * q + 3] = fmaf(v1, ww.w, acc1[4 * q + 3]);
       }
     }
     uint32_t o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      __half2 h = __floats2half2_rn(fmaxf(acc0[j].x, 0.0f), fmaxf(acc0[j].y, 0.0f));
+      __half2 h = __floats2half2_rn(fmaxf(acc0[2 * j], 0.0f), fmaxf(acc0[2 * j + 1], 0.0f));
       o[j] = *reinterpret_cast<uint32_t*>(&h);
     }
     stg_v8(out + c0, o);                                   // 16 channels = one full 32-byte sector
     if (two) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        __half2 h = __floats2half2_rn(fmaxf(acc1[j].x, 0.0f), fmaxf(acc1[j].y, 0.0f));
+        __half2 h = __floats2half2_rn(fmaxf(acc1[2 * j], 0.0f), fmaxf(acc1[2 * j + 1], 0.0f));
         o[j] = *reinterpret_cast<uint32_t*>(&h);
       }
       stg_v8(out + STEM_CO + c0, o);
@@ -133,17 +134,13 @@ struct CombineParams {
   int relu;
 };
 
-// a[0..8) += wgt * (8 fp16 channels of q): packed fp32x2 FMAs (sm_100 FFMA2: two IEEE fused multiply-adds per
-// instruction, same rounding as eight scalar fmaf) - the kernel is bound by instruction issue
 __device__ __forceinline__ void acc8(float* a, const uint4 q, float wgt) {
   const uint32_t r[4] = {q.x, q.y, q.z, q.w};
-  const float2 w2 = make_float2(wgt, wgt);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r[j]));
-    const float2 d = __ffma2_rn(w2, f, make_float2(a[2 * j], a[2 * j + 1]));
-    a[2 * j] = d.x;
-    a[2 * j + 1] = d.y;
+    a[2 * j] = fmaf(wgt, f.x, a[2 * j]);
+    a[2 * j + 1] = fmaf(wgt, f.y, a[2 * j + 1]);
   }
 }
 

@@ -296,7 +296,8 @@ CAL_HD inline void set_pose(CamState* cam, const double* R, const double* t) {
 // (from the pose in *cam when `keep_init`, else from the ground-plane homography of the matches).
 // ws.pnp_status: 1 reproduced the reference's pose, 0 the RANSAC failed (fallback pose).
 // (the n matches are in ws.pnp_obj / ws.pnp_px, float32-rounded; K and the start pose in *cam)
-CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, CamState* cam, bool keep_init) {
+CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, CamState* cam, bool keep_init,
+                                           bool refine_follows = false) {
   if (T.tid == 0) {
     ws.pnp_status = 0; ws.pnp_best = -1; ws.pnp_maxgood = 0; ws.pnp_niters = 100;
     ws.pnp_mask = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
@@ -463,11 +464,12 @@ CAL_HD_NOINLINE inline void solve_pnp_core(const Team& T, Workspace& ws, int n, 
   }
   const bool ok = cam->ok != 0;
   T.sync();
-  if (ok) refine_camera_masked(T, ws, n, ws.pnp_mask, cam);
+  // (the caller's refine_camera over the same matches follows: its least squares starts from this pose)
+  if (ok && !refine_follows) refine_camera_masked(T, ws, n, ws.pnp_mask, cam);
 }
 
 CAL_HD inline void solve_pnp(const Team& T, Workspace& ws, const CalSolveParams& P, const Points& pts, CamState* cam,
-                             bool keep_init) {
+                             bool keep_init, bool refine_follows = false) {
   if (T.tid == 0) {
     for (int k = 0; k < pts.n; ++k) {
       const double* w = P.pitch_xyz + 3 * pts.id[k];
@@ -476,7 +478,7 @@ CAL_HD inline void solve_pnp(const Team& T, Workspace& ws, const CalSolveParams&
     }
   }
   T.sync();
-  solve_pnp_core(T, ws, pts.n, cam, keep_init);
+  solve_pnp_core(T, ws, pts.n, cam, keep_init, refine_follows);
 }
 
 // Camera.projection_rmse (camera.py:249-277): mean L2 distance; project_point rounds the
@@ -621,7 +623,7 @@ CAL_HD_NOINLINE inline void homography_camera(const Team& T, Workspace& ws, cons
   const bool ok = ws.hom.ok != 0;
   T.sync();
   if (!ok) return;
-  solve_pnp(T, ws, P, pts, &ws.hom, true);
+  solve_pnp(T, ws, P, pts, &ws.hom, true, true);
   const bool pnp_ok = ws.hom.ok != 0;
   T.sync();
   if (pnp_ok) refine_camera(T, ws, P, pts, &ws.hom);
@@ -643,7 +645,7 @@ CAL_HD_NOINLINE inline double all_points_camera(const Team& T, Workspace& ws, co
   // n_groundplane is always 2 there (len of a dict): solve_pnp always runs.  The calibrated
   // pose of a ground-plane view 0 is the natural initial pose; a goal-plane view 0 lives in
   // swapped coordinates, so start from the ground homography instead.
-  solve_pnp(T, ws, P, pts, &ws.cam, first_plane == 0);
+  solve_pnp(T, ws, P, pts, &ws.cam, first_plane == 0, pts.n > 6);
   const bool pnp_ok = ws.cam.ok != 0;
   T.sync();
   if (pnp_ok && pts.n > 6) refine_camera(T, ws, P, pts, &ws.cam);

@@ -43,6 +43,10 @@ constexpr int NKP = CAL_NUM_KEYPOINTS;   // 57
 constexpr int MAXV = 3;                  // planar views: ground plane, left goal, right goal
 constexpr int MAXOBS = 80;               // 53 + 10 + 10 observations at most
 constexpr int MAXP = 1 + 6 * MAXV;       // f + 3 poses
+#ifndef LM_STEP_TOL
+#define LM_STEP_TOL 1e-11
+#define LM_COST_TOL 1e-14
+#endif
 constexpr int NHYP = 512;                // RANSAC hypotheses evaluated per round (scratch size)
 
 struct Team {
@@ -464,7 +468,7 @@ CAL_HD_NOINLINE inline void lm_solve(const Team& T, Workspace& ws, int max_iter)
           const double dc = ws.cost - ws.cand_cost;
           ws.f = ws.cand_f;
           for (int v = 0; v < ws.nviews; ++v) ws.pose[v] = ws.cand_pose[v];
-          ws.flag = (md < 1e-11 || dc <= 1e-14 * ws.cost) ? 2 : 1;
+          ws.flag = (md < LM_STEP_TOL || dc <= LM_COST_TOL * ws.cost) ? 2 : 1;
           ws.cost = ws.cand_cost;
           ws.lambda = fmax(ws.lambda * 0.1, 1e-15);
         } else {

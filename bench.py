@@ -366,6 +366,17 @@ def run_b200(args, rank, world, local_rank):
             "algorithmic_tflop_per_step": conv_tflop, "share_of_step": conv_ms / (ms / args.steps), "traffic": None,
             "timing": "CUDA events around every launch of one extra single-stream step (the timed steps overlap the "
                       "two networks on two streams, so share_of_step can exceed what a serial step would show)"}
+    # counter-backed DRAM traffic of the step's largest conv bucket (one ncu --set full capture, tools/ncu_shapes.py ->
+    # tools/summarize_profiles.py -> profiles/traffic.json), per launch, next to the algorithmic bytes of that launch
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and (nh, nw) == (H_IMG, W_IMG) and B == 64:
+        tj = json.load(open(tpath))
+        if tj.get("launches"):
+            top = tj["launches"][0]
+            roof["traffic"] = top["dram_bytes"]
+            roof["traffic_detail"] = {"launch": f"{top['kernel']} {top['shape']} (the largest bucket of the step)",
+                                      "algorithmic_bytes": top["algorithmic_bytes"], "source": tj["source"],
+                                      "all": [{k: l[k] for k in ("shape", "dram_bytes", "algorithmic_bytes")} for l in tj["launches"]]}
     dec = {}
     if "kp_decode" in per:
         bytes_alg = B * 57 * ((nh + 1) // 2) * ((nw + 1) // 2) * 4

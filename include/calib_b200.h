@@ -286,6 +286,14 @@ int cal_debug_mn_mma(const void* x_128x64, const void* y_64x128, int mode, float
  * entry per CTA. */
 int cal_debug_mma_rate(int N, int shift_rows, int iters, int flags, long long* out_cycles, void* stream);
 
+/* Experiment: cycles per tile of the tcgen05.mma trains the 3x3 kernels issue (csrc/probe.cu), in isolation:
+ * pattern 0 = filter-row grouping (N = 2n and N = n per filter row), 1 = the same with a fixed A address,
+ * 2 = nine N = n taps, 3 = three taps side by side (N = 3n), 4 = N = 2n throughout, 5 = N = 256, 6 = pattern 0
+ * with the N = 2n trains first; nk = K steps per chunk; flags: bit 0 = random operands (else zeros), bit 1 = two
+ * tcgen05.commit per tile, bit 2 = four warps reading TMEM meanwhile, bits 8-11 = accumulators rotated over. */
+int cal_debug_mma_pattern(int pattern, int n, int nk, int iters, int flags, int ctas, long long* out_cycles,
+                          void* stream);
+
 /* ------------------------------------------------------------------ metric -- */
 
 /* The official camera-calibration metric on the GPU, one thread block per frame: the step after the path,

@@ -15,7 +15,7 @@ EXPORTS = [
     "cal_stem_conv", "cal_stem_conv_u8", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points", "cal_evaluate_cameras", "cal_hrnet_weight_count", "cal_hrnet_create", "cal_hrnet_forward",
     "cal_hrnet_output_shape", "cal_hrnet_launches", "cal_hrnet_destroy",
-    "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate",
+    "cal_debug_tma_probe", "cal_debug_shift_mma", "cal_debug_mn_mma", "cal_debug_mma_rate", "cal_debug_mma_pattern",
 ]
 
 
@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
     L.cal_debug_shift_mma.argtypes = [vp, vp, i32, i32, vp, vp]
     L.cal_debug_mn_mma.argtypes = [vp, vp, i32, vp, vp]
     L.cal_debug_mma_rate.argtypes = [i32, i32, i32, i32, vp, vp]
+    L.cal_debug_mma_pattern.argtypes = [i32, i32, i32, i32, i32, i32, vp, vp]
     L.cal_camera_solve.argtypes = [vp, vp, C.POINTER(SolveParams), i32, vp, vp]
     L.cal_pnp_refine.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     L.cal_pnp_solve.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]

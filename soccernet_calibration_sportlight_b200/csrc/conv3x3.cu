@@ -299,6 +299,28 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (DX) {
           // per filter row: [taps dx = 1 | dx = 0] from the view shifted by dy rows, then tap dx = 2 from
           // the view one pixel further into the first group's accumulator columns
+          if (p.ablate & 64) {
+            if (do_mma) {
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const uint32_t at = a_lo + tap_off[dy * 3];
+                const uint32_t bl = w_cc + dy * 3 * w_tap;
+                umma_f16_lo(d_tmem, at, bl, dhi, idesc2, (cc | dy) != 0);
+                if (nk > 1) umma_f16_lo(d_tmem, at + 2, bl + 2, dhi, idesc2, 1);
+                if (nk > 2) umma_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc2, 1);
+                if (nk > 3) umma_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc2, 1);
+              }
+#pragma unroll
+              for (int dy = 0; dy < 3; ++dy) {
+                const uint32_t at1 = a_lo + tap_off[dy * 3 + 1];
+                const uint32_t bl2 = w_cc + dy * 3 * w_tap + 2 * w_tap;
+                umma_f16_lo(d_tmem, at1, bl2, dhi, idesc, 1);
+                if (nk > 1) umma_f16_lo(d_tmem, at1 + 2, bl2 + 2, dhi, idesc, 1);
+                if (nk > 2) umma_f16_lo(d_tmem, at1 + 4, bl2 + 4, dhi, idesc, 1);
+                if (nk > 3) umma_f16_lo(d_tmem, at1 + 6, bl2 + 6, dhi, idesc, 1);
+              }
+            }
+          } else
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             if (do_mma) {
@@ -546,9 +568,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t o[8];
           if (cb * 16 < p.mma_n) {
             uint32_t g1[16], g0[16];
+            if (p.ablate & 32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { g1[j] = 0u; g0[j] = 0u; }
+            } else {
             tmem_ld16(taddr + cb * 16, g1);
             tmem_ld16(taddr + p.mma_n + cb * 16, g0);
             tmem_ld_wait();
+            }
             const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             const float4* bb4 = reinterpret_cast<const float4*>(s_bias + tc.n0 + cb * 16);

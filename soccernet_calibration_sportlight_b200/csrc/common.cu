@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#define CAL_TU "common.cu"
 #include "common.cuh"
 
 namespace cal {

@@ -80,15 +80,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifndef CAL_TU
+#define CAL_TU "?"
+#endif
+__device__ __forceinline__ void mbar_wait_at(uint64_t* bar, uint32_t parity, int line) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
-      printf("cal: mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      printf("cal: mbarrier wait timeout at %s:%d (block %d of %d, thread %d, parity %u)\n", CAL_TU, line, blockIdx.x,
+             gridDim.x, threadIdx.x, parity);
       __trap();
     }
   }
 }
+#define mbar_wait(bar, parity) mbar_wait_at(bar, parity, __LINE__)
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

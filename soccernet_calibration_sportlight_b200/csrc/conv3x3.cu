@@ -38,12 +38,14 @@
 // weights are resident): the old per-tap kernel ran these layers at the L2 throughput cap.
 #include <stdlib.h>
 
+#define CAL_TU "conv3x3.cu"
 #include "common.cuh"
 
 namespace cal {
 namespace {
 
-constexpr int H_THREADS = 320;            // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int H_THREADS = 352;            // warp 0 producer, warp 1 MMA, warps 2..9 epilogue, warp 10 second MMA issuer
+constexpr int H_MMA2_WARP = 10;
 constexpr int H_EPI_THREADS = 256;
 constexpr int H_MAX_A_STAGES = 6;
 constexpr int H_MAX_B_STAGES = 12;
@@ -72,6 +74,7 @@ struct HaloParams {
   int w_slices;            // weights are slice-major: slice s = rows [s*Cout_rows, (s+1)*Cout_rows) of a (.., 64) matrix
   int cout_rows;
   int relu, ablate;     // ablate: profiling experiments only (CAL_DEBUG_ABLATE), 0 in production
+  int dual;             // two MMA-issuing warps: 1 = they alternate items (T = 1), 2 = they split the tiles of every item (T > 1)
   int dx;               // filter-row grouping: taps dx = 1, 0 in one N = 2 * mma_n MMA, the column shift in the epilogue (template DX)
   int a_stages, a_stage_bytes, out_bufs;
   uint32_t a_tx_bytes;
@@ -127,11 +130,12 @@ __device__ __forceinline__ uint32_t h_pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <bool RESIDENT, int T, bool DX = false>
+template <bool RESIDENT, int T, int DXB = 0>   // DXB: filter-row grouping with mma_n = 16 * DXB output channels (0: off)
 __global__ void __launch_bounds__(H_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmBp, const __grid_constant__ CUtensorMap tmY,
                     const HaloParams p) {
+  constexpr bool DX = DXB > 0;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -160,10 +164,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
-    for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], p.cluster); }
+    const uint32_t n_iss = p.dual == 2 ? 2u : 1u;         // issuers committing on every shared stage
+    for (int s = 0; s < H_MAX_A_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], n_iss); }
+    for (int s = 0; s < H_MAX_B_STAGES; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], p.cluster * n_iss); }
     mbar_init(wfull, 1);
-    for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], T > 1 ? 4 * T : 4); }
+    for (int a = 0; a < H_MAX_ACC; ++a) { mbar_init(&tfull[a], n_iss); mbar_init(&tempty[a], T > 1 ? 4 * T : 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, H_TMEM_COLS);
@@ -243,13 +248,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (warp == H_MMA2_WARP && p.dual)) {
+    // -------------------------------------------------------------- MMA issuer(s)
+    // The issuing thread is the scarce resource of the small-N layers: the tensor pipe queues only a couple
+    // of MMAs, so every barrier round trip of the issuing thread (~200 cycles) and every instruction between
+    // two MMAs shows up as idle tensor time (tools/gpu_mma_pattern.py: the filter-row grouped train of a
+    // C = 48 tile takes 1780 cycles from one thread with the loop's waits, 1150 from two threads on
+    // alternate tiles = the tensor pipe's own time).  With p.dual a second warp issues as well: dual == 1,
+    // the two alternate the CTA's items (own accumulator and operand stages, nothing shared); dual == 2,
+    // both walk every item and every weight stage and issue one tile each of the item's T tiles (the
+    // shared stages are released by both).
     // The whole warp walks the (warp-uniform) schedule and one elected lane issues. N is 48..192
     // here, an MMA retires every 44..96 cycles and the tensor pipe queues only a couple of them
     // (tools/gpu_mma_rate.py), so the loop between two MMAs has to be a handful of instructions:
     // everything is hoisted into registers, the descriptors advance by 32-bit adds on their low
     // word, the tap order and the tiles per item are compile-time constants.
+    const int iw = warp == 1 ? 0 : 1;
+    const bool alt = p.dual == 1, split = p.dual == 2;
     int sa = 0, sb = 0, as = 0;
     uint32_t pha = 0, phb = 0, aphase = 0;
     const uint32_t idesc = make_idesc_f16(128, p.mma_n);
@@ -262,7 +277,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool issuer = elect_one();
     const bool do_mma = issuer && !(p.ablate & 4);
     const bool mc = p.cluster > 1;
-    const bool stamp = p.dbg != nullptr && issuer;
+    const bool stamp = p.dbg != nullptr && issuer && iw == 0;
     if (RESIDENT) { mbar_wait(wfull, 0); tc_fence_after(); }
     const uint32_t a_lo0 = dlo + ((smem_u32(sA) & 0x3FFFF) >> 4), a_step = static_cast<uint32_t>(p.a_stage_bytes) >> 4;
     const uint32_t w_lo0 = dlo + ((smem_u32(sW) & 0x3FFFF) >> 4), w_step = static_cast<uint32_t>(p.b_slice_bytes) >> 4;
@@ -279,8 +294,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int mi = 0;
     bool pre = false;        // this item's tempty / first fullA were already waited for (see below)
     for (int t = blockIdx.x; t < total; t += step, ++mi) {
+      if (alt && (mi & 1) != iw) {
+        // the other issuer's item: step the rings past it
+        for (int cc = 0; cc < ncc; ++cc) { a_lo += a_step; if (++sa == a_stages) { sa = 0; pha ^= 1; a_lo = a_lo0; } }
+        if (++as == n_acc) { as = 0; aphase ^= 1; }
+        continue;
+      }
       if (stamp) H_STAMP(1, mi, 0);
-      const bool has_next = t + step < total;
+      const bool has_next = !p.dual && t + step < total;      // look-ahead waits: single issuer only (the other issuer covers them)
       bool pre_next = false;
       if (!pre) {
         mbar_wait(&tempty[as], aphase ^ 1);
@@ -359,6 +380,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t first = (cc | t9) != 0;
 #pragma unroll
             for (int tl = 0; tl < T; ++tl) {                 // the tiles of the item share the slice
+              if (T > 1 && split && (tl & 1) != iw) continue;
               const uint32_t al = at + tl * a_tile1;
               const uint32_t dt = d_tmem + tl * acc_stride;
               umma_f16_lo(dt, al, bl, dhi, idesc, first);
@@ -412,7 +434,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++as == n_acc) { as = 0; aphase ^= 1; }
       pre = pre_next;
     }
-  } else {
+  } else if (warp < H_MMA2_WARP) {
     // ---------------------------------------------------------------- epilogue
     // Two groups of four warps ping-pong over the tiles: group g owns TMEM accumulator stage g
     // and staging buffer g, so the latency chain of one tile's epilogue (TMEM load, residual
@@ -480,8 +502,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 8; ++q) rdx[q] = make_uint4(0, 0, 0, 0);
         if (rrow) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            if (q * 8 < p.mma_n) rdx[q] = ldg_nc_v4(rrow + q * 8);
+          for (int q = 0; q < 2 * DXB; ++q) rdx[q] = ldg_nc_v4(rrow + q * 8);
+        }
+        if (p.res) {
+          // this group's next tile: its residual rows start their way from HBM to L2 now (one 128-byte line
+          // per pixel), so the loads above find them there a tile from now
+          const __half* rn = residual_row(t + t_step, tn);
+          if (rn) asm volatile("prefetch.global.L2 [%0];" ::"l"(rn));
         }
       }
       uint4 rpre[8];
@@ -558,24 +585,40 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           *reinterpret_cast<uint4*>(blk + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       };
-      if (DX) {
+      if constexpr (DX) {
         // out[p] = G0[p] + G1'[p + 1]: the two column groups of the accumulator, the shift by a warp
         // shuffle (a patch row of TWp <= 32 pixels lies inside this warp's lanes; the lanes whose
-        // neighbour belongs to the next row are halo columns, which are not stored)
-        // 16-channel blocks of the output pixel (Cout_pad = 64: four)
+        // neighbour belongs to the next row are halo columns, which are not stored).  The epilogue is a
+        // latency chain (TMEM load -> shuffle -> math -> store) that two groups of warps have to get
+        // through once per tile time: all the tile's TMEM loads go out together, the accumulator stage is
+        // handed back as soon as they have landed, and the arithmetic runs on registers only.
+        constexpr int NBP = DXB == 1 ? 1 : 2;                  // 16-channel blocks per pass (64 accumulator registers; three blocks at once spilled and measured slower)
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          uint32_t o[8];
-          if (cb * 16 < p.mma_n) {
-            uint32_t g1[16], g0[16];
-            if (p.ablate & 32) {
+        for (int b0 = 0; b0 < DXB; b0 += NBP) {
+          uint32_t g1[16 * NBP], g0[16 * NBP];
+          if (p.ablate & 32) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { g1[j] = 0u; g0[j] = 0u; }
-            } else {
-            tmem_ld16(taddr + cb * 16, g1);
-            tmem_ld16(taddr + p.mma_n + cb * 16, g0);
-            tmem_ld_wait();
+            for (int j = 0; j < 16 * NBP; ++j) { g1[j] = 0u; g0[j] = 0u; }
+          } else {
+#pragma unroll
+            for (int b = 0; b < NBP; ++b) {
+              if (b0 + b < DXB) {
+                tmem_ld16(taddr + (b0 + b) * 16, g1 + 16 * b);
+                tmem_ld16(taddr + 16 * DXB + (b0 + b) * 16, g0 + 16 * b);
+              }
             }
+            tmem_ld_wait();
+          }
+          if (b0 + NBP >= DXB) {                                // accumulator drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+          }
+#pragma unroll
+          for (int b = 0; b < NBP; ++b) {
+            const int cb = b0 + b;
+            if (cb >= DXB) break;
+            uint32_t o[8];
             const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             const float4* bb4 = reinterpret_cast<const float4*>(s_bias + tc.n0 + cb * 16);
@@ -586,21 +629,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {
                 const int j = j4 * 2 + h2;
-                float a = __uint_as_float(g0[2 * j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j]), 1);
-                float b = __uint_as_float(g0[2 * j + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[2 * j + 1]), 1);
+                float a = __uint_as_float(g0[16 * b + 2 * j]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[16 * b + 2 * j]), 1);
+                float bvv = __uint_as_float(g0[16 * b + 2 * j + 1]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g1[16 * b + 2 * j + 1]), 1);
                 const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
                 a += bv[2 * h2] + __low2float(rh);
-                b += bv[2 * h2 + 1] + __high2float(rh);
-                if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
-                o[j] = h_pack_half2(a, b);
+                bvv += bv[2 * h2 + 1] + __high2float(rh);
+                if (p.relu) { a = fmaxf(a, 0.0f); bvv = fmaxf(bvv, 0.0f); }
+                o[j] = h_pack_half2(a, bvv);
               }
             }
-          } else {
-            // pad channels stay zero
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = 0u;
+            if (valid && !(p.ablate & 2)) stg_v8(yrow + cb * 16, o);
           }
-          if (valid && !(p.ablate & 2)) stg_v8(yrow + cb * 16, o);
+        }
+        if (valid && !(p.ablate & 2)) {
+          // pad channels stay zero
+          const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int cb = DXB; cb < 4; ++cb) stg_v8(yrow + cb * 16, z);
         }
       } else {
         for (int g = 0; g < groups_total; ++g) {
@@ -628,9 +673,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (leader) H_STAMP(2 + grp, ei, 5);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
+      if (!DX) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);            // accumulator drained
+      }
       if (staged) {
         fence_proxy_async();                              // staging writes -> visible to the TMA unit
         if (leader) H_STAMP(2 + grp, ei, 6);
@@ -676,7 +723,7 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   // filter-row grouping (template DX) applies to the single-chunk, single-N-tile layers (C <= 64 in and out);
   // it needs a patch row inside one warp (TWp <= 32)
   static const bool dx_enabled = [] { const char* e = getenv("CAL_CONV_DX"); return !(e && e[0] == '0'); }();
-  const bool dx_shape = dx_enabled && a->Cin_pad == 64 && a->Cout_pad == 64 && a->Cout_rows % 8 == 0;
+  const bool dx_shape = dx_enabled && a->Cin_pad == 64 && a->Cout_pad == 64 && (a->Cout_rows == 32 || a->Cout_rows == 48 || a->Cout_rows == 64);
   long best = -1;
   for (int twp = 16; twp <= (dx_shape ? 32 : 128); twp *= 2) {
     const int tw = twp - 2, r = 128 / twp;
@@ -819,7 +866,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -835,6 +884,16 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
       p.cluster = cl; p.part_rows = p.mma_n / cl; p.n_slowest = n_tiles > 1 ? 1 : 0;
       break;
     }
+  }
+  // two MMA-issuing warps (see the kernel): alternate items for the resident T = 1 variants, one tile each of
+  // the T = 2 items; the streamed T = 1 layers (N = 192: the MMAs are long enough for one thread) keep one
+  static const int dual_mask = [] { const char* e = getenv("CAL_CONV_DUAL"); return e ? atoi(e) : 3; }();
+  p.dual = 0;
+  if (p.cluster == 1) {
+    // (alternating items: the second issuer's waits run ncc stages ahead of the first's; a parity wait is only
+    // meaningful within one pass of the ring)
+    if (p.T == 1 && p.w_resident && 2 * p.ncc <= p.a_stages && p.n_acc >= 2 && (dual_mask & 1)) p.dual = 1;
+    if (p.T == 2 && (dual_mask & 2)) p.dual = 2;
   }
   const int w_slots = p.w_resident ? 9 * p.ncc : p.b_stages * p.G;
   const size_t smem = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes +
@@ -874,9 +933,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
     static const bool show = getenv("CAL_DEBUG_CONFIG") != nullptr;
     if (show)
       fprintf(stderr, "halo conv %dx%d Cin_pad %d Cout_pad %d: N_tile %d G %d TWp %d R %d T %d resident %d a_stages %d b_stages %d "
-                      "slice %d B n_acc %d cluster %d smem %zu grid %d items %d dx %d\n",
+                      "slice %d B n_acc %d cluster %d smem %zu grid %d items %d dx %d dual %d\n",
               a->Hout, a->Wout, a->Cin_pad, a->Cout_pad, p.N_tile, p.G, p.TWp, p.R, p.T, p.w_resident, p.a_stages, p.b_stages,
-              p.b_slice_bytes, p.n_acc, p.cluster, smem, grid, p.total_tiles, p.dx);
+              p.b_slice_bytes, p.n_acc, p.cluster, smem, grid, p.total_tiles, p.dx, p.dual);
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
@@ -892,7 +951,9 @@ int launch_conv3x3_halo(const CalConvArgs* a, void* stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  if (p.w_resident && p.dx) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1, true>, tmA, tmB, tmBp, tmY, p));
+  if (p.w_resident && p.dx && p.mma_n == 32) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1, 2>, tmA, tmB, tmBp, tmY, p));
+  else if (p.w_resident && p.dx && p.mma_n == 48) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1, 3>, tmA, tmB, tmBp, tmY, p));
+  else if (p.w_resident && p.dx) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1, 4>, tmA, tmB, tmBp, tmY, p));
   else if (p.w_resident && p.T == 2) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 2>, tmA, tmB, tmBp, tmY, p));
   else if (p.w_resident) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<true, 1>, tmA, tmB, tmBp, tmY, p));
   else if (p.T == 4) CAL_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_halo_kernel<false, 4>, tmA, tmB, tmBp, tmY, p));

@@ -21,12 +21,14 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#define CAL_TU "conv_tc.cu"
 #include "common.cuh"
 
 namespace cal {
 namespace {
 
-constexpr int CONV_THREADS = 320;          // 10 warps
+constexpr int CONV_THREADS = 352;          // 11 warps: producer, MMA issuer, 8 epilogue warps, second MMA issuer
+constexpr int CONV_MMA2_WARP = 10;
 constexpr int A_STAGE_BYTES = 128 * 128;   // 128 rows x 64 fp16
 constexpr int KC = 64;                     // K elements per pipeline stage
 constexpr int MAX_STAGES = 8;
@@ -42,6 +44,8 @@ struct ConvParams {
   int kc_per_tap, taps, stride, pad, num_k;
   int ksteps_last;   // K = 16 steps of the last channel chunk that hold real channels
   int relu, mode, n_classes;
+  int dual;          // two MMA-issuing warps take alternate tiles (the issuing thread's barrier round trips are the
+                     // bottleneck of short K loops: csrc/probe.cu, tools/gpu_mma_pattern.py); CAL_TC_DUAL=0 turns it off
   int wait_ahead;    // MMA issuer: next stage's wait before this stage's commit (experiments: CAL_TC_WAIT_AHEAD=0)
   int stages, b_stage_bytes;
   int n_acc, acc_stride;
@@ -125,10 +129,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
-    // -------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || (warp == CONV_MMA2_WARP && p.dual)) {
+    // -------------------------------------------------------------- MMA issuer(s)
     // warp-uniform schedule, one elected lane issues: descriptors stay in uniform registers
-    int stage = 0, as = 0;
+    const int iw = warp == 1 ? 0 : 1;
+    int stage = 0, as = 0, it = 0;
     uint32_t phase = 0, aphase = 0;
     const uint32_t idesc = make_idesc_f16(128, p.mma_n);
     const uint64_t desc0 = make_smem_desc(0, 128, 2);
@@ -138,7 +143,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int num_k = p.num_k, stages = p.stages, kc_per_tap = p.kc_per_tap, ksteps_last = p.ksteps_last, n_acc = p.n_acc;
     const bool issuer = elect_one();
     bool ready = false;          // this stage's full barrier was already waited for
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      if (p.dual && (it & 1) != iw) {
+        // the other issuer's tile: step the rings past it
+        for (int k = 0; k < num_k; ++k)
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        if (++as == n_acc) { as = 0; aphase ^= 1; }
+        continue;
+      }
       mbar_wait(&tempty[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * p.acc_stride;
@@ -171,7 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (++as == n_acc) { as = 0; aphase ^= 1; }
     }
-  } else {
+  } else if (warp < CONV_MMA2_WARP) {
     // ---------------------------------------------------------------- epilogue
     // Two groups of four warps ping-pong over the tiles (group g owns accumulator stage g), so
     // one tile's TMEM-load / residual-read / store chain overlaps the other group's.
@@ -595,6 +607,12 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   CAL_REQUIRE(stages >= 2, CAL_E_UNSUPPORTED, "cal_conv2d: tile does not fit shared memory");
   p.stages = stages;
+  // (opt-in, CAL_TC_DUAL=1: the full pipeline failed intermittently with it - unspecified launch failure in the first
+  // processes on a box - and the 1x1 convs it applies to are bandwidth-bound anyway)
+  { static const bool du = [] { const char* e = getenv("CAL_TC_DUAL"); return e && e[0] == '1'; }(); p.dual = (du && p.n_acc >= 2) ? 1 : 0; }
+  // the second issuer waits on barriers up to num_k positions ahead of the first's, and a parity wait is only
+  // meaningful within one pass of the ring: short K loops only (the 1x1 convs)
+  if (p.num_k + 1 > stages) p.dual = 0;
   { static const bool wa = [] { const char* e = getenv("CAL_TC_WAIT_AHEAD"); return !(e && e[0] == '0'); }(); p.wait_ahead = wa ? 1 : 0; }
   p.tx_bytes = (uint32_t)(p.TW * p.TH * 128 + p.mma_n * 128);
   const size_t smem = 1024 + (size_t)stages * stage_bytes + tail_bytes;

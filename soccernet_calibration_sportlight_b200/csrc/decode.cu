@@ -14,6 +14,7 @@
 // per plane.
 #include <math_constants.h>
 
+#define CAL_TU "decode.cu"
 #include "common.cuh"
 
 namespace cal {

@@ -9,6 +9,7 @@
 //                     (hrnet.py:229-246) and the head's upsample (hrnet.py:489-509);
 //                     bilinear, align_corners=True, coordinates as in
 //                     torch.nn.functional.interpolate.  HBM-bound, 128-bit accesses.
+#define CAL_TU "elementwise.cu"
 #include "common.cuh"
 
 namespace cal {

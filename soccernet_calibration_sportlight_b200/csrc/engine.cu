@@ -19,6 +19,7 @@
 #include <string>
 #include <vector>
 
+#define CAL_TU "engine.cu"
 #include "common.cuh"
 
 namespace cal {

@@ -4,6 +4,7 @@
 // border fall on the same side.
 #include <math_constants.h>
 
+#define CAL_TU "evaluate.cu"
 #include "common.cuh"
 
 namespace cal {

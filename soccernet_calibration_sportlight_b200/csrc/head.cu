@@ -15,6 +15,7 @@
 // depends only on the tile position, so each persistent CTA builds it once per position and
 // sweeps the batch.  Neither the upsampled projections (13.8 GB at batch 64) nor the
 // concatenated tensor ever exist.
+#define CAL_TU "head.cu"
 #include "common.cuh"
 
 namespace cal {

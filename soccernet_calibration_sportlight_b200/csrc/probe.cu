@@ -3,6 +3,7 @@
 // cal_debug_mma_pattern: cycles per "tile" for the tcgen05.mma trains the 3x3 kernels issue, measured in
 // isolation (one warp issuing, operands resident in shared memory, optional epilogue-like TMEM readers):
 // which part of a tile's issue time is the instruction mix itself.
+#define CAL_TU "probe.cu"
 #include "common.cuh"
 
 namespace cal {

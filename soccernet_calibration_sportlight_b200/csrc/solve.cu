@@ -5,6 +5,7 @@
 // solve_core.cuh / solve_cascade.cuh; here are the kernels and the C ABI.
 #include <math_constants.h>
 
+#define CAL_TU "solve.cu"
 #include "common.cuh"
 #include "solve_cascade.cuh"
 

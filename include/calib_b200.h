@@ -103,6 +103,25 @@ typedef struct CalConvArgs {
  * (hrnet.py:42-58, 79-99, 184-213, 260-266, 316-330, 366-388). */
 int cal_conv2d(const CalConvArgs* h_args, void* stream);
 
+typedef struct CalBasicBlockArgs {
+  const void* x;      /* fp16 NHWC (B, H, W, 64): the block input, also its residual */
+  const void* w1;     /* fp16 slice-major (9, rows, 64): conv1 + bn1 folded (CalConvArgs.w with w_slices = 1) */
+  const float* bias1; /* fp32 (64) */
+  const void* w2;     /* conv2 + bn2, same layout */
+  const float* bias2;
+  void* y;            /* fp16 NHWC (B, H, W, 64) */
+  int32_t B, H, W;
+  int32_t C_pad;      /* 64 */
+  int32_t rows;       /* weight rows per tap: the channel count rounded up to 16 (16, 32 or 48) */
+  int32_t C;          /* real channels (K steps over pad lanes are skipped) */
+} CalBasicBlockArgs;
+
+/* BasicBlock.forward (src/models/hrnet/hrnet.py:29-58) with inplanes == planes <= 48 and no downsample, in one
+ * kernel: y = relu(bn2(conv2(relu(bn1(conv1(x))))) + x), the intermediate tensor held in shared memory (half the
+ * HBM traffic of two cal_conv2d launches, bit-identical results).  CAL_E_UNSUPPORTED for other shapes: the
+ * caller runs the two convs. */
+int cal_basicblock(const CalBasicBlockArgs* h_args, void* stream);
+
 /* Stem conv1: 3x3 stride-2 conv 3->64 + BN + ReLU straight from the fp32 NCHW
  * frame tensor (hrnet.py:450-452).  x: (B,3,H,W) fp32 in [0,1] BGR;
  * w: fp32 (64, 27) BN folded [co][ci*9+ky*3+kx]; y: fp16 NHWC (B,Ho,Wo,64). */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcalib_b200.so")
 CAL_MAX_SOURCES = 6
 
 EXPORTS = [
-    "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d",
+    "cal_abi_version", "cal_last_error", "cal_set_smem_headroom", "cal_kp_decode", "cal_line_decode", "cal_conv2d", "cal_basicblock",
     "cal_stem_conv", "cal_stem_conv_u8", "cal_fuse_combine", "cal_head_fused", "cal_camera_solve", "cal_pnp_refine", "cal_pnp_solve",
     "cal_line_points", "cal_evaluate_cameras", "cal_hrnet_weight_count", "cal_hrnet_create", "cal_hrnet_forward",
     "cal_hrnet_output_shape", "cal_hrnet_launches", "cal_hrnet_destroy",
@@ -30,6 +30,12 @@ class ConvArgs(C.Structure):
                 ("Hout", C.c_int32), ("Wout", C.c_int32), ("Cout_pad", C.c_int32),
                 ("Cout_rows", C.c_int32), ("ksize", C.c_int32), ("stride", C.c_int32),
                 ("relu", C.c_int32), ("mode", C.c_int32), ("n_classes", C.c_int32), ("Cin", C.c_int32), ("w_slices", C.c_int32)]
+
+
+class BasicBlockArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w1", C.c_void_p), ("bias1", C.c_void_p), ("w2", C.c_void_p), ("bias2", C.c_void_p),
+                ("y", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C_pad", C.c_int32), ("rows", C.c_int32), ("C", C.c_int32)]
 
 
 class CombineArgs(C.Structure):
@@ -97,6 +103,7 @@ def lib() -> C.CDLL:
     L.cal_kp_decode.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp]
     L.cal_line_decode.argtypes = [vp, i32, i32, i32, i32, f64, f32, vp, vp]
     L.cal_conv2d.argtypes = [C.POINTER(ConvArgs), vp]
+    L.cal_basicblock.argtypes = [C.POINTER(BasicBlockArgs), vp]
     L.cal_stem_conv.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cal_stem_conv_u8.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.cal_fuse_combine.argtypes = [C.POINTER(CombineArgs), vp]

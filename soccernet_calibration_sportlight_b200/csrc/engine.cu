@@ -14,6 +14,7 @@
 // same schedule op by op through the single-op entry points and is kept as the readable twin - the two are
 // required to agree bit for bit (tests/test_engine_gpu.py).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -333,8 +334,39 @@ struct Run {
     return y;
   }
 
+  // Both convs of a BasicBlock of the full-resolution branch in one kernel (basicblock.cu); false when the shape
+  // is served by the two launches.
+  bool basicblock(const Tensor& x, Block& b, Tensor* out) {
+    static const bool enabled = [] { const char* e = getenv("CAL_BASICBLOCK"); return !(e && e[0] == '0'); }();
+    if (!enabled || b.ds >= 0 || b.convs.size() != 2) return false;
+    Conv& c1 = n.convs[b.convs[0]];
+    Conv& c2 = n.convs[b.convs[1]];
+    for (const Conv* c : {&c1, &c2})
+      if (!(c->slices && c->k == 3 && c->s == 1 && c->cin_pad == 64 && c->cout_pad == 64 && c->rows <= 48)) return false;
+    if (x.C != 64 || c1.rows != c2.rows || c1.cin != c2.cin) return false;
+    Tensor y = alloc(x.B, x.H, x.W, 64);
+    if (rc != CAL_OK) return false;
+    CalBasicBlockArgs a{};
+    a.x = x.p; a.w1 = c1.w; a.bias1 = c1.b; a.w2 = c2.w; a.bias2 = c2.b; a.y = y.p;
+    a.B = x.B; a.H = x.H; a.W = x.W; a.C_pad = 64; a.rows = c1.rows; a.C = c1.cin;
+    const int r = cal_basicblock(&a, st);
+    if (r == CAL_OK) { ++n.launches; *out = y; return true; }
+    release(y);
+    if (r != CAL_E_UNSUPPORTED) rc = r;
+    return false;
+  }
+
   Tensor blocks(Tensor x, std::vector<Block>& bl, bool own_x) {
     for (Block& b : bl) {
+      {
+        Tensor y;
+        if (basicblock(x, b, &y)) {
+          if (own_x) release(x);
+          x = y; own_x = true;
+          continue;
+        }
+        if (rc != CAL_OK) break;
+      }
       Tensor r = x;
       bool own_r = false;
       if (b.ds >= 0) { r = conv(x, n.convs[b.ds], false, nullptr); own_r = true; }

@@ -329,6 +329,7 @@ class HRNetHeatmap:
         self.fused_head = os.environ.get("CAL_FUSED_HEAD", "1") != "0"
         self.chained_head = os.environ.get("CAL_HEAD_CHAIN", "1") != "0"
         self.slice_major = os.environ.get("CAL_W_SLICES", "1") != "0"
+        self.fuse_blocks = os.environ.get("CAL_BASICBLOCK", "1") != "0"     # cal_basicblock for the C <= 48 BasicBlocks
         self.branch_streams = os.environ.get("CAL_BRANCH_STREAMS", "0") != "0"   # measured neutral: off
         self._streams: List[torch.cuda.Stream] = []
         # the forward through the library's own engine (csrc/engine.cu: cal_hrnet_create / cal_hrnet_forward),
@@ -517,8 +518,29 @@ class HRNetHeatmap:
                 p.w = p.w_k
         return ops.conv2d(x, p.w, p.b, y, ksize=p.k, stride=p.s, cout_rows=p.rows, relu=relu, res=res, cin=p.cin)
 
+    def _basicblock(self, x, convs):
+        """Both convs of a BasicBlock of the full-resolution branch in one kernel (csrc/basicblock.cu); None when
+        the shape is served by the two launches."""
+        if not self.fuse_blocks or len(convs) != 2:
+            return None
+        p1, p2 = self._packed[convs[0].conv], self._packed[convs[1].conv]
+        ok = all(p.slices and p.k == 3 and p.s == 1 and p.cin_pad == 64 and p.cout_pad == 64 and p.rows <= 48 for p in (p1, p2))
+        if not ok or x.shape[-1] != 64 or p1.rows != p2.rows or p1.cin != p2.cin:
+            return None
+        try:
+            return ops.basicblock(x, p1.w, p1.b, p2.w, p2.b, torch.empty_like(x), rows=p1.rows, c=p1.cin)
+        except ops._lib.CalError as e:
+            if "status -2" not in str(e):
+                raise
+            return None
+
     def _blocks(self, x, blocks):
         for convs, ds in blocks:
+            if ds is None:
+                y = self._basicblock(x, convs)
+                if y is not None:
+                    x = y
+                    continue
             r = x if ds is None else self._conv(x, ds.conv, relu=False)
             t = x
             for c in convs[:-1]:

@@ -130,6 +130,31 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], y: to
     return y
 
 
+def basicblock(x: torch.Tensor, w1: torch.Tensor, bias1: torch.Tensor, w2: torch.Tensor, bias2: torch.Tensor,
+               y: torch.Tensor, *, rows: int, c: int) -> torch.Tensor:
+    """BasicBlock.forward (hrnet.py:29-58) in one kernel: x, y fp16 NHWC (B,H,W,64); w1, w2 slice-major
+    (9, rows, 64); raises CalError(status CAL_E_UNSUPPORTED) for shapes the two-launch path serves."""
+    B, H, W, Cp = x.shape
+    if tuple(y.shape) != tuple(x.shape):
+        raise _lib.CalError("basicblock: output shape mismatch")
+    for w in (w1, w2):
+        if tuple(w.shape) != (9, rows, 64):
+            raise _lib.CalError(f"basicblock: slice-major weight shape {tuple(w.shape)}")
+    a = _lib.BasicBlockArgs()
+    a.x = _dev(x, torch.float16, "basicblock x")
+    a.w1 = _dev(w1, torch.float16, "basicblock w1")
+    a.w2 = _dev(w2, torch.float16, "basicblock w2")
+    a.bias1 = _dev(bias1, torch.float32, "basicblock bias1")
+    a.bias2 = _dev(bias2, torch.float32, "basicblock bias2")
+    a.y = _dev(y, torch.float16, "basicblock y")
+    a.B, a.H, a.W, a.C_pad, a.rows, a.C = B, H, W, Cp, rows, int(c)
+    name = "basicblock" if PROFILE is None else f"basicblock C{c} @{H}x{W}"
+    with _Launch(name, x.device):
+        st = _lib.lib().cal_basicblock(C.byref(a), _stream())
+    _lib.check(st, "cal_basicblock")
+    return y
+
+
 def stem_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """x fp32 NCHW (B,3,H,W) in [0,1], or uint8 NHWC (B,H,W,3) as cv2.imread leaves it (ToTensor's /255 folded
     into the load); w fp32 (64,27); y fp16 NHWC (B,Ho,Wo,64)."""

@@ -32,7 +32,7 @@ def test_engine_equals_python_schedule(kind, H, W, B):
     b = py(x)[-1]
     n_py = ops.LAUNCHES - n0
     assert a.shape == b.shape and torch.equal(a, b)
-    assert n_eng == n_py and n_eng > 300                     # the same launches, counted on both sides
+    assert n_eng == n_py and n_eng > 250                     # the same launches, counted on both sides
     assert torch.equal(eng(x)[-1], a)                        # and again (allocator reuse)
 
 

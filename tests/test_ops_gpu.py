@@ -2,6 +2,8 @@
 the same op on the fp16-rounded operands (isolates accumulation order; fp32 accumulate on
 tcgen05).  Tolerance: 2e-3 * max(1, |ref|_max) + 1e-3 absolute - fp16 output rounding
 (2^-11 relative) plus summation-order noise; (log)softmax outputs 2e-3 absolute."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -205,3 +207,54 @@ def test_head_fused_vs_torch(B, H, W, lows, cout):
     assert out2 is not None and bool(torch.isfinite(out2).all())
     e2 = (out2.cpu() - ref2).abs()
     assert float(e2.max()) <= (0.05 if mode == 1 else 5e-3), float(e2.max())
+
+
+BLOCK_CASES = [
+    dict(B=1, H=8, W=16, c=48),
+    dict(B=2, H=13, W=50, c=48),            # ragged rows and columns, two strips per frame
+    dict(B=1, H=135, W=240, c=48),          # the network's own shape
+    dict(B=3, H=21, W=61, c=32),
+    dict(B=2, H=17, W=30, c=18),            # w18 config: 18 channels in 32 weight rows
+    dict(B=40, H=9, W=140, c=48),           # 200 strips: several per CTA, every ring slot sees every chunk position
+    dict(B=1, H=4, W=28, c=16),
+]
+
+
+@pytest.mark.parametrize("case", BLOCK_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_basicblock_matches_the_two_launches(case):
+    """cal_basicblock (conv - ReLU - conv - add - ReLU with the intermediate in shared memory) against the two
+    cal_conv2d launches it replaces (bit for bit with CAL_BB_TAP3=0, where it issues the same MMAs in the same
+    order), and against fp32."""
+    B, H, W, c = case["B"], case["H"], case["W"], case["c"]
+    g = torch.Generator().manual_seed(7 + H + W)
+    x = torch.randn(B, c, H, W, generator=g)
+    ws, bs, packed = [], [], []
+    for _ in range(2):
+        w = torch.randn(c, c, 3, 3, generator=g) * (1.0 / (c * 9) ** 0.5)
+        b = torch.randn(c, generator=g) * 0.1
+        wp, bp, rows = packing.pack_conv(w.double(), b.double())
+        packed.append((wp.reshape(rows, -1, 64).permute(1, 0, 2).contiguous().to(dev), bp.to(dev), rows))
+        ws.append(w.to(torch.float16).float().to(dev)); bs.append(b.to(dev))
+    xh = packing.to_nhwc16(x.to(dev))
+    rows = packed[0][2]
+    t = torch.full_like(xh, float("nan"))
+    ops.conv2d(xh, packed[0][0], packed[0][1], t, ksize=3, stride=1, cout_rows=rows, relu=True, cin=c, w_slices=True)
+    y_two = torch.full_like(xh, float("nan"))
+    ops.conv2d(t, packed[1][0], packed[1][1], y_two, ksize=3, stride=1, cout_rows=rows, relu=True, res=xh, cin=c, w_slices=True)
+    y = torch.full_like(xh, float("nan"))
+    ops.basicblock(xh, packed[0][0], packed[0][1], packed[1][0], packed[1][1], y, rows=rows, c=c)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(y).all())
+    assert bool((y[..., c:] == 0).all()), "channel padding lanes must be written as zero"
+    diff = float((y.float() - y_two.float()).abs().max())
+    if os.environ.get("CAL_BB_TAP3", "0") != "1":
+        assert torch.equal(y, y_two), f"max |diff| {diff:.3e}"      # filter-row grouping of conv3x3.cu: same MMAs, same order
+    else:
+        # three taps per MMA: the taps of a filter row are summed after, not inside, the accumulation - fp32 rounding
+        # differences that survive the fp16 store as at most an ulp or two
+        assert diff <= 2e-3 * max(1.0, float(y_two.float().abs().max())), f"max |diff| {diff:.3e}"
+    xr = packing.from_nhwc16(xh, c)
+    mid = F.relu(F.conv2d(xr, ws[0], bs[0], padding=1)).to(torch.float16).float()
+    ref = F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + xr)
+    err = float((packing.from_nhwc16(y, c) - ref).abs().max())
+    assert err <= 4e-3 * max(1.0, float(ref.abs().max())) + 2e-3, f"max err {err:.3e}"

@@ -48,6 +48,7 @@ struct BBParams {
   const float* bias2;
   const __half* x;
   __half* y;
+  int ablate;                    // profiling experiments only (CAL_DEBUG_ABLATE): 4 = issue no MMAs, 2 = no global stores, 32 = no TMEM loads
   long long* dbg;                // profiling experiments only (CAL_DEBUG_TIMELINE): cycles each role spent waiting, per CTA
 };
 
@@ -69,52 +70,50 @@ __device__ __forceinline__ uint32_t bb_pack_half2(float a, float b) {
 }
 
 
-// One pass of an epilogue over NBP 16-channel blocks of this thread's pixel: all their TMEM loads go out together,
-// `loaded()` runs once they have landed (the last pass hands the accumulator stage back there), then the filter-row
-// groups are combined in registers: v = G0[p] + G1[p + 1] (+ G2[p + 2]), the pixel shifts as warp shuffles (a patch
-// row is the warp's 32 lanes; the lanes whose neighbour belongs to the next row are halo columns nobody stores).
-template <int NB, bool TAP3, int NBP, typename F>
-__device__ __forceinline__ void bb_acc_pass(uint32_t taddr, int b0, float (&v)[16 * NBP], F&& loaded) {
-  if constexpr (!TAP3 && NBP == NB) {
-    // the whole [G1 | G0] accumulator (32 * NB columns) in NB wide loads and one wait: the epilogue is a latency
-    // chain per step (TMEM load -> shuffle -> math -> store), so the fewer round trips the better
-    uint32_t acc[32 * NB];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) tmem_ld32(taddr + 32 * i, acc + 32 * i);
-    tmem_ld_wait();
-    loaded();
-#pragma unroll
-    for (int c = 0; c < 16 * NB; ++c)
-      v[c] = __uint_as_float(acc[16 * NB + c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(acc[c]), 1);
-    return;
-  } else {
+// The NB 16-channel blocks of this thread's pixel, software-pipelined: the TMEM loads of block cb + 1 are in
+// flight while block cb is combined and finished (the TMEM read port delivers 64 B/clk per SM - 768 cycles for a
+// step's [G1 | G0] accumulator - and both epilogues share it: it must not idle while an epilogue does arithmetic).
+// `loaded()` runs once the last load has landed, `block(cb, v)` gets v = G0[p] + G1[p + 1] (+ G2[p + 2]).
+template <int NB, bool TAP3, typename FL, typename FB>
+__device__ __forceinline__ void bb_acc_blocks(uint32_t taddr, int ablate, FL&& loaded, FB&& block) {
+  const bool no_ld = (ablate & 32) != 0;
   constexpr int G = TAP3 ? 3 : 2;
-  uint32_t g[G][16 * NBP];
+  uint32_t g[2][G][16];
+  if (no_ld) {
 #pragma unroll
-  for (int bb = 0; bb < NBP; ++bb) {
-    if (b0 + bb < NB) {
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int gi = 0; gi < G; ++gi) tmem_ld16(taddr + gi * 16 * NB + (b0 + bb) * 16, g[gi] + 16 * bb);
-    }
+      for (int gi = 0; gi < G; ++gi)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) g[i][gi][c] = 0u;
   }
-  tmem_ld_wait();
-  loaded();
+  if (!no_ld) {
 #pragma unroll
-  for (int bb = 0; bb < NBP; ++bb) {
-    if (b0 + bb < NB) {
+    for (int gi = 0; gi < G; ++gi) tmem_ld16(taddr + gi * 16 * NB, g[0][gi]);
+  }
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int i = 16 * bb + c;
-        if (TAP3) {
-          float a = __uint_as_float(g[0][i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g[1][i]), 1);
-          v[i] = a + __shfl_down_sync(0xffffffffu, __uint_as_float(g[2][i]), 2);
-        } else {
-          // accumulator columns [G1 | G0] (conv3x3.cu)
-          v[i] = __uint_as_float(g[1][i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g[0][i]), 1);
-        }
+  for (int cb = 0; cb < NB; ++cb) {
+    if (!no_ld) tmem_ld_wait();
+    if (cb + 1 < NB) {
+      if (!no_ld) {
+#pragma unroll
+        for (int gi = 0; gi < G; ++gi) tmem_ld16(taddr + gi * 16 * NB + (cb + 1) * 16, g[(cb + 1) & 1][gi]);
+      }
+    } else {
+      loaded();
+    }
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      if (TAP3) {
+        const float a = __uint_as_float(g[cb & 1][0][c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g[cb & 1][1][c]), 1);
+        v[c] = a + __shfl_down_sync(0xffffffffu, __uint_as_float(g[cb & 1][2][c]), 2);
+      } else {
+        // accumulator columns [G1 | G0] (conv3x3.cu)
+        v[c] = __uint_as_float(g[cb & 1][1][c]) + __shfl_down_sync(0xffffffffu, __uint_as_float(g[cb & 1][0][c]), 1);
       }
     }
-  }
+    block(cb, v);
   }
 }
 
@@ -215,6 +214,7 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
     const uint32_t d0 = tmem_base + cv * 2 * ACC;
     const int nk = p.nk;
     const bool issuer = elect_one();
+    const bool do_mma = !(p.ablate & 4);
     mbar_wait(wfull, 0);
     tc_fence_after();
     int slot = 0, as = 0;
@@ -230,6 +230,7 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
         if (issuer) {
           const uint32_t d = d0 + as * ACC;
           const uint32_t a_lo = a_lo0 + slot * (BB_CH >> 4);
+          if (do_mma)
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const uint32_t at = a_lo + ((dy * BB_TWP * 128) >> 4), at1 = at + (128 >> 4);
@@ -277,52 +278,40 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
         tc_fence_after();
         constexpr int ACC = TAP3 ? BB_ACC3 : BB_ACC;
         const uint32_t taddr = tmem_base + as * ACC + (static_cast<uint32_t>(quarter * 32) << 16);
-        uint4 o4[2 * NB];
-        constexpr int NBP = TAP3 ? 1 : NB;
-#pragma unroll
-        for (int b0 = 0; b0 < NB; b0 += NBP) {
-          float v[16 * NBP];
-          bb_acc_pass<NB, TAP3, NBP>(taddr, b0, v, [&] {
-            if (b0 + NBP >= NB) {                                  // accumulator drained
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&t1empty[as]);
-            }
-          });
-#pragma unroll
-          for (int bb = 0; bb < NBP; ++bb) {
-            const int cb = b0 + bb;
-            if (cb >= NB) break;
-            uint32_t o[8];
-            const float4* bb4 = reinterpret_cast<const float4*>(s_bias + cb * 16);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bq = bb4[j4];
-              const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int jj = j4 * 2 + h2;
-                float a = v[16 * bb + 2 * jj], c = v[16 * bb + 2 * jj + 1];
-                a += bv[2 * h2] + 0.0f;                          // (the separate launch adds bias + residual(= 0) the same way)
-                c += bv[2 * h2 + 1] + 0.0f;
-                a = fmaxf(a, 0.0f); c = fmaxf(c, 0.0f);
-                o[jj] = inside ? bb_pack_half2(a, c) : 0u;
-              }
-            }
-            o4[2 * cb] = make_uint4(o[0], o[1], o[2], o[3]);
-            o4[2 * cb + 1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        }
         // the chunk's slot must have been read for the last time (conv2 three steps back)
         BB_WAIT(&midEmpty[slot], ph ^ 1, 1);
         uint8_t* row = sMid + slot * BB_CH + m * 128;
+        uint8_t* mrow = sMid + BB_SLOTS * BB_CH + m * 128;
+        const bool mirror = slot == 0 && m < BB_MIR_ROWS;
+        bb_acc_blocks<NB, TAP3>(taddr, p.ablate, [&] {
+          tc_fence_before();                                     // accumulator drained
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t1empty[as]);
+        }, [&](int cb, const float (&v)[16]) {
+          uint32_t o[8];
+          const float4* bb4 = reinterpret_cast<const float4*>(s_bias + cb * 16);
 #pragma unroll
-        for (int q = 0; q < 2 * NB; ++q) *reinterpret_cast<uint4*>(row + ((q ^ (m & 7)) << 4)) = o4[q];
-        if (slot == 0 && m < BB_MIR_ROWS) {
-          uint8_t* mrow = sMid + BB_SLOTS * BB_CH + m * 128;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bq = bb4[j4];
+            const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
-          for (int q = 0; q < 2 * NB; ++q) *reinterpret_cast<uint4*>(mrow + ((q ^ (m & 7)) << 4)) = o4[q];
-        }
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int jj = j4 * 2 + h2;
+              float a = v[2 * jj], c = v[2 * jj + 1];
+              a += bv[2 * h2] + 0.0f;                          // (the separate launch adds bias + residual(= 0) the same way)
+              c += bv[2 * h2 + 1] + 0.0f;
+              a = fmaxf(a, 0.0f); c = fmaxf(c, 0.0f);
+              o[jj] = inside ? bb_pack_half2(a, c) : 0u;
+            }
+          }
+          const uint4 lo = make_uint4(o[0], o[1], o[2], o[3]), hi = make_uint4(o[4], o[5], o[6], o[7]);
+          *reinterpret_cast<uint4*>(row + (((2 * cb) ^ (m & 7)) << 4)) = lo;
+          *reinterpret_cast<uint4*>(row + (((2 * cb + 1) ^ (m & 7)) << 4)) = hi;
+          if (mirror) {
+            *reinterpret_cast<uint4*>(mrow + (((2 * cb) ^ (m & 7)) << 4)) = lo;
+            *reinterpret_cast<uint4*>(mrow + (((2 * cb + 1) ^ (m & 7)) << 4)) = hi;
+          }
+        });
         fence_proxy_async();                          // chunk -> visible to the tensor core's shared-memory reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&midFull[slot]);
@@ -357,43 +346,32 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
         constexpr int ACC = TAP3 ? BB_ACC3 : BB_ACC;
         const uint32_t taddr = tmem_base + (2 + as) * ACC + (static_cast<uint32_t>(quarter * 32) << 16);
         __half* yrow = p.y + pix * 64;
-        constexpr int NBP = TAP3 ? 1 : NB;
+        bb_acc_blocks<NB, TAP3>(taddr, p.ablate, [&] {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t2empty[as]);
+        }, [&](int cb, const float (&v)[16]) {
+          uint32_t o[8];
+          const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          const float4* bb4 = reinterpret_cast<const float4*>(s_bias + 64 + cb * 16);
 #pragma unroll
-        for (int b0 = 0; b0 < NB; b0 += NBP) {
-          float v[16 * NBP];
-          bb_acc_pass<NB, TAP3, NBP>(taddr, b0, v, [&] {
-            if (b0 + NBP >= NB) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&t2empty[as]);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bq = bb4[j4];
+            const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int jj = j4 * 2 + h2;
+              float a = v[2 * jj], c = v[2 * jj + 1];
+              const __half2 rh = *reinterpret_cast<const __half2*>(&rr[jj]);
+              a += bv[2 * h2] + __low2float(rh);
+              c += bv[2 * h2 + 1] + __high2float(rh);
+              if (p.relu_out) { a = fmaxf(a, 0.0f); c = fmaxf(c, 0.0f); }
+              o[jj] = bb_pack_half2(a, c);
             }
-          });
-#pragma unroll
-          for (int bb = 0; bb < NBP; ++bb) {
-            const int cb = b0 + bb;
-            if (cb >= NB) break;
-            uint32_t o[8];
-            const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            const float4* bb4 = reinterpret_cast<const float4*>(s_bias + 64 + cb * 16);
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bq = bb4[j4];
-              const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int jj = j4 * 2 + h2;
-                float a = v[16 * bb + 2 * jj], c = v[16 * bb + 2 * jj + 1];
-                const __half2 rh = *reinterpret_cast<const __half2*>(&rr[jj]);
-                a += bv[2 * h2] + __low2float(rh);
-                c += bv[2 * h2 + 1] + __high2float(rh);
-                if (p.relu_out) { a = fmaxf(a, 0.0f); c = fmaxf(c, 0.0f); }
-                o[jj] = bb_pack_half2(a, c);
-              }
-            }
-            if (valid) stg_v8(yrow + cb * 16, o);
           }
-        }
+          if (valid && !(p.ablate & 2)) stg_v8(yrow + cb * 16, o);
+        });
         if (valid) {
           const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // pad channels stay zero
 #pragma unroll
@@ -443,6 +421,7 @@ extern "C" int cal_basicblock(const CalBasicBlockArgs* a, void* stream) {
   p.bias1 = a->bias1; p.bias2 = a->bias2;
   p.x = reinterpret_cast<const __half*>(a->x);
   p.y = reinterpret_cast<__half*>(a->y);
+  { const char* e = getenv("CAL_DEBUG_ABLATE"); p.ablate = e ? atoi(e) : 0; }
   { const char* e = getenv("CAL_DEBUG_TIMELINE"); p.dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr; }
   const size_t smem = 1024 + 2 * static_cast<size_t>(BB_RING) + 2 * static_cast<size_t>(p.w_bytes) + 32 * 8 + 16 + 128 * 4;
   if (smem > static_cast<size_t>(227 * 1024 - smem_headroom())) {

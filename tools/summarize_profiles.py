@@ -76,13 +76,13 @@ def shapes():
         return
     import json
     sys.path.insert(0, os.path.join(ROOT, "tools"))
-    names = ["3x3 48->48 @135x240", "3x3 48->48 @135x240 +residual", "3x3 96->96 @68x120", "3x3 96->96 @68x120 +residual",
+    names = ["BasicBlock 48 @135x240 (conv-ReLU-conv-add-ReLU in one kernel)", "3x3 48->48 @135x240", "3x3 48->48 @135x240 +residual", "3x3 96->96 @68x120", "3x3 96->96 @68x120 +residual",
              "3x3 192->192 @34x60", "3x3 384->384 @17x30", "1x1 64->256 @135x240 +residual"]
     # algorithmic bytes per launch at batch 64: input + output (+ residual) in fp16 NHWC with the padded channel count
     B = 64
-    alg = [B * 135 * 240 * 64 * 2 * 2, B * 135 * 240 * 64 * 2 * 3, B * 68 * 120 * 128 * 2 * 2, B * 68 * 120 * 128 * 2 * 3,
+    alg = [B * 135 * 240 * 64 * 2 * 2, B * 135 * 240 * 64 * 2 * 2, B * 135 * 240 * 64 * 2 * 3, B * 68 * 120 * 128 * 2 * 2, B * 68 * 120 * 128 * 2 * 3,
            B * 34 * 60 * 192 * 2 * 2, B * 17 * 30 * 384 * 2 * 2, B * 135 * 240 * (64 + 256 + 256) * 2]
-    flop = [2 * B * 135 * 240 * 48 * 48 * 9] * 2 + [2 * B * 68 * 120 * 96 * 96 * 9] * 2 + [2 * B * 34 * 60 * 192 * 192 * 9,
+    flop = [4 * B * 135 * 240 * 48 * 48 * 9] + [2 * B * 135 * 240 * 48 * 48 * 9] * 2 + [2 * B * 68 * 120 * 96 * 96 * 9] * 2 + [2 * B * 34 * 60 * 192 * 192 * 9,
             2 * B * 17 * 30 * 384 * 384 * 9, 2 * B * 135 * 240 * 64 * 256]
     txt = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
@@ -91,7 +91,7 @@ def shapes():
     out = []
     with open(os.path.join(PROF, f"{tag}_shapes_ncu_full.csv"), "w") as f:
         f.write("# ncu --set full --clock-control none --nvtx --nvtx-include cap/ : one warm launch of each dominant conv shape at batch 64 "
-                "(tools/ncu_shapes.py); algorithmic bytes = input + output (+ residual) once, fp16 NHWC, padded channels\n")
+                "(tools/ncu_shapes.py); algorithmic bytes = input + output (+ residual) once, fp16 NHWC, padded channels (the fused BasicBlock: block input + block output; the two launches it replaces: 530.8 + 796.3 MB)\n")
         f.write("shape,kernel,duration_us,dram_read_MB,dram_write_MB,algorithmic_MB,traffic_over_algorithmic,dram_pct_of_peak,"
                 "tensor_pipe_pct_elapsed,algorithmic_TFLOPs_per_s,registers,smem_dynamic_KB\n")
         for i, r in enumerate(rows[2:]):

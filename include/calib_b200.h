@@ -143,6 +143,7 @@ typedef struct CalCombineArgs {
   int32_t src_w[CAL_MAX_SOURCES];
   const float* bias;                /* optional fp32 (C_pad) */
   int32_t relu;
+  int32_t C;                        /* real channels (0 = C_pad): the pad lanes are written as zeros without being gathered */
 } CalCombineArgs;
 
 /* y = [relu]( bias + sum_i up_i(src_i) ): the multi-resolution fuse of

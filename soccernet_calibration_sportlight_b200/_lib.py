@@ -45,7 +45,7 @@ class CombineArgs(C.Structure):
                 ("src", C.c_void_p * CAL_MAX_SOURCES),
                 ("src_h", C.c_int32 * CAL_MAX_SOURCES),
                 ("src_w", C.c_int32 * CAL_MAX_SOURCES),
-                ("bias", C.c_void_p), ("relu", C.c_int32)]
+                ("bias", C.c_void_p), ("relu", C.c_int32), ("C", C.c_int32)]
 
 
 class HeadArgs(C.Structure):

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_conv_kernel(const void* __r
 struct CombineParams {
   __half* y;
   int B, H, W, C8;       // C8 = C_pad / 8 (uint4 lanes per pixel)
+  int C8r;               // lanes that hold real channels, rounded up to the lanes per thread: the rest are written as zeros
   int n_src;
   const __half* src[CAL_MAX_SOURCES];
   int sh[CAL_MAX_SOURCES], sw[CAL_MAX_SOURCES];
@@ -161,7 +162,8 @@ template <int LANES>
 __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineParams p) {
   const int b = blockIdx.z;
   const int y_base = blockIdx.y * FC_TY, x_base = blockIdx.x * FC_TX;
-  const int lanes = p.C8 / LANES;                 // threads per pixel
+  const int lanes = p.C8r / LANES;                // threads per pixel (the pad lanes are not worth threads: they would sit
+                                                  // masked in every warp - the kernel is bound by instruction issue)
   const int ppb = FC_THREADS / lanes;             // pixels per pass
   const int tid = threadIdx.x;
   if (tid >= ppb * lanes) return;
@@ -230,6 +232,9 @@ __global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineP
         o[j] = *reinterpret_cast<uint32_t*>(&h);
       }
       out[(y * p.W + x) * p.C8 + l] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (c8 + LANES == p.C8r) {                    // the pixel's last thread: pad lanes stay zero
+      for (int l = LANES; c8 + l < p.C8; ++l) out[(y * p.W + x) * p.C8 + l] = make_uint4(0u, 0u, 0u, 0u);
     }
   }
 }
@@ -300,6 +305,11 @@ extern "C" int cal_fuse_combine(const CalCombineArgs* a, void* stream) {
   for (int i = 0; i < a->n_src; ++i)
     CAL_REQUIRE(static_cast<long long>(a->src_h[i]) * a->src_w[i] * p.C8 < (1ll << 31), CAL_E_UNSUPPORTED,
                 "cal_fuse_combine: source %d too large for 32-bit offsets", i);
+  {
+    const int c = (a->C > 0 && a->C <= a->C_pad) ? a->C : a->C_pad;
+    const int per = p.C8 % 2 == 0 ? 2 : 1;          // lanes per thread
+    p.C8r = ((c + 7) / 8 + per - 1) / per * per;
+  }
   if (p.C8 % 2 == 0)
     fuse_combine_kernel<2><<<grid, FC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(p);
   else

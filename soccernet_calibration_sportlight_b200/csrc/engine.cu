@@ -387,8 +387,9 @@ struct Run {
     return x;
   }
 
-  int combine(Tensor& y, const std::vector<Tensor>& srcs, const float* bias, bool relu) {
+  int combine(Tensor& y, const std::vector<Tensor>& srcs, const float* bias, bool relu, int c_real = 0) {
     CalCombineArgs a{};
+    a.C = c_real;
     a.y = y.p; a.B = y.B; a.H = y.H; a.W = y.W; a.C_pad = y.C; a.n_src = (int)srcs.size();
     for (size_t i = 0; i < srcs.size(); ++i) { a.src[i] = srcs[i].p; a.src_h[i] = srcs[i].H; a.src_w[i] = srcs[i].W; }
     a.bias = bias; a.relu = relu ? 1 : 0;
@@ -425,7 +426,7 @@ struct Run {
         std::vector<Tensor> srcs = {r};
         for (int j = i + 1; j < nb; ++j) srcs.push_back(conv(xs[j], n.convs[m.fuse[i][j][0]], false, nullptr));
         Tensor y = alloc(xs[i].B, xs[i].H, xs[i].W, xs[i].C);
-        if (rc == CAL_OK) { const int r2 = combine(y, srcs, nullptr, true); if (r2 != CAL_OK) rc = r2; }
+        if (rc == CAL_OK) { const int r2 = combine(y, srcs, nullptr, true, n.convs[m.fuse[i][i + 1][0]].cout); if (r2 != CAL_OK) rc = r2; }
         for (size_t q = 1; q < srcs.size(); ++q) release(srcs[q]);
         if (own_r) release(r);
         r = y; own_r = true;

@@ -585,7 +585,7 @@ class HRNetHeatmap:
             if has_up:
                 ups = [self._conv(xs[j], fuse[i][j][0].conv, relu=False) for j in range(i + 1, nb)]
                 y = torch.empty_like(xs[i])
-                r = ops.fuse_combine(y, [r] + ups, None, relu=True)
+                r = ops.fuse_combine(y, [r] + ups, None, relu=True, c=fuse[i][i + 1][0].cout)
             outs.append(r)
         return outs
 

@@ -173,9 +173,10 @@ def stem_conv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, y: torch.Ten
 
 
 def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[torch.Tensor] = None,
-                 relu: bool = False) -> torch.Tensor:
+                 relu: bool = False, c: int = 0) -> torch.Tensor:
     """y = [relu](bias + sum_i up_i(src_i)); all fp16 NHWC with the same C_pad; sources of a
-    different spatial size are bilinearly resampled (align_corners=True)."""
+    different spatial size are bilinearly resampled (align_corners=True).  c = real channels (0: C_pad): the
+    pad lanes are written as zeros without being gathered."""
     B, H, W, Cp = y.shape
     a = _lib.CombineArgs()
     a.y = _dev(y, torch.float16, "combine y")
@@ -190,6 +191,7 @@ def fuse_combine(y: torch.Tensor, srcs: Sequence[torch.Tensor], bias: Optional[t
         a.src_h[i], a.src_w[i] = s.shape[1], s.shape[2]
     a.bias = _dev(bias, torch.float32, "combine bias") if bias is not None else None
     a.relu = int(relu)
+    a.C = int(c)
     name = "fuse_combine" if PROFILE is None else f"fuse_combine n{len(srcs)} C{Cp} @{H}x{W}"
     with _Launch(name, y.device):
         st = _lib.lib().cal_fuse_combine(C.byref(a), _stream())

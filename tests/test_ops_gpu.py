@@ -258,3 +258,22 @@ def test_basicblock_matches_the_two_launches(case):
     ref = F.relu(F.conv2d(mid, ws[1], bs[1], padding=1) + xr)
     err = float((packing.from_nhwc16(y, c) - ref).abs().max())
     assert err <= 4e-3 * max(1.0, float(ref.abs().max())) + 2e-3, f"max err {err:.3e}"
+
+
+@pytest.mark.parametrize("c,cp", [(48, 64), (96, 128), (18, 64), (40, 64)])
+def test_fuse_combine_skips_pad_lanes(c, cp):
+    """With the real channel count given, the pad lanes are written as zeros without being gathered: same bits as the
+    full-width launch on sources whose pad lanes are zero."""
+    g = torch.Generator().manual_seed(c)
+    B, H, W = 2, 19, 37
+    srcs = []
+    for (h, w) in ((H, W), (10, 19), (5, 10)):
+        t = torch.zeros(B, h, w, cp, dtype=torch.float16)
+        t[..., :c] = torch.randn(B, h, w, c, generator=g).half()
+        srcs.append(t.to(dev))
+    y0 = torch.full((B, H, W, cp), float("nan"), dtype=torch.float16, device=dev)
+    y1 = torch.full_like(y0, float("nan"))
+    ops.fuse_combine(y0, srcs, None, relu=True)
+    ops.fuse_combine(y1, srcs, None, relu=True, c=c)
+    assert bool(torch.isfinite(y1).all()) and bool((y1[..., c:] == 0).all())
+    assert torch.equal(y0, y1)

@@ -42,4 +42,8 @@ for spec in "head:head_:2:2" "combine:fuse_combine:40:3" "decode:kp_decode:1:1" 
 done
 fi
 tail -3 $OUT/${TAG}_bench_full.err
+# gpurun brings back at most 64 MiB: condense the ncu reports here (profiles/ layout under gpurun_out/prof_<tag>) and drop them
+CAL_PROF_DIR=$OUT/prof_${TAG} python tools/summarize_profiles.py ${TAG} full > $OUT/${TAG}_summarize.txt 2>&1
+rm -f $OUT/${TAG}_*.ncu-rep
 ls $OUT | grep ${TAG} | tr '\n' ' '
+du -sh $OUT

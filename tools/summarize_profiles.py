@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.environ.get("CAL_PROF_DIR", os.path.join(ROOT, "profiles"))   # CAL_PROF_DIR: summarise on the GPU box into gpurun_out/
 tag = sys.argv[1]
 wl = sys.argv[2] if len(sys.argv) > 2 else "kp_decode"
 os.makedirs(PROF, exist_ok=True)

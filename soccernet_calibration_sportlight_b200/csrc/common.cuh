@@ -39,6 +39,9 @@ int encode_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t
 
 // conv3x3.cu: halo-tile kernel for 3x3 stride-1 convs; CAL_E_UNSUPPORTED = use the generic kernel
 int launch_conv3x3_halo(const CalConvArgs* a, void* stream);
+// conv3x3_pair.cu: CTA-pair kernel (cta_group::2, half of the weights resident per CTA) for the layers whose weights
+// do not fit one CTA; CAL_E_UNSUPPORTED = not such a layer
+int launch_conv3x3_pair(const CalConvArgs* a, void* stream);
 // Programmatic dependent launch between the path's own kernels (opt-in: CAL_PDL=1).
 bool pdl_enabled();
 // bytes of shared memory per SM the persistent kernels leave to a co-resident camera-solve block

@@ -556,6 +556,8 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
     // 3x3 stride-1 layers: halo-tile kernel (conv3x3.cu); CAL_CONV_HALO=0 forces the generic one
     static const bool use_halo = [] { const char* e = getenv("CAL_CONV_HALO"); return !(e && e[0] == '0'); }();
     if (use_halo) {
+      const int rcp = launch_conv3x3_pair(a, stream);
+      if (rcp != CAL_E_UNSUPPORTED) return rcp;
       const int rc = launch_conv3x3_halo(a, stream);
       if (rc != CAL_E_UNSUPPORTED) return rc;
     }

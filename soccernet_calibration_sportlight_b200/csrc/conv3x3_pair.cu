@@ -24,15 +24,19 @@ namespace {
 constexpr int P_THREADS = 352;            // warp 0 TMA producer, warps 1 and 10 MMA issuers (leader CTA), warps 2..9 epilogue
 constexpr int P_MMA2_WARP = 10;
 constexpr int P_STAGES = 4;               // input patch ring
-constexpr int P_ACC = 4;                  // accumulator stages in TMEM (128 columns each)
-constexpr int P_ACC_STRIDE = 128;
+constexpr int P_ACC = 4;                  // accumulator stages in TMEM at most (512 columns / N tile)
+constexpr int P_G = 3;                    // weight slices per ring stage (streamed mode): one barrier pair per stage
+constexpr int P_MAX_B = 6;
 constexpr int P_TWP = 32, P_TW = 30, P_R = 4;
 constexpr uint32_t P_PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
 
 struct PairParams {
   int B, H, W, Cout_pad;
   int tiles_x, tiles_y, total_tiles, items;
-  int rows, half_rows, ncc, nk_last;
+  int rows, half_rows, ncc, nk_last;   // rows = N of an MMA (the N tile); half_rows of every slice live in each CTA
+  int rows_total, n_tiles;             // weight rows per slice in the tensor; N tiles (Cout = n_tiles * rows)
+  int resident;                        // all half-slices resident, or streamed through a ring of `b_stages` stages of P_G slices
+  int b_stages, b_stage_bytes, n_acc, acc_stride;
   int relu;
   int dual;                // second MMA-issuing warp (alternate items); needs 2 * ncc <= P_STAGES: a parity wait is only meaningful within one pass of the ring
   int a_stage_bytes, half_bytes;
@@ -86,9 +90,13 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & P_PEER_MASK) : "memory");
 }
 
-struct PTile { int b, y0, x0; bool real; };
-__device__ __forceinline__ PTile p_tile(const PairParams& p, int t) {
+struct PTile { int b, y0, x0, n0; bool real; };
+// item -> (N tile, pair of pixel tiles); this CTA takes pixel tile 2 * (it / n_tiles) + rank
+__device__ __forceinline__ PTile p_tile(const PairParams& p, int it, int rank) {
   PTile c;
+  const int nt = it % p.n_tiles;
+  const int t = 2 * (it / p.n_tiles) + rank;
+  c.n0 = nt * p.rows;
   c.real = t < p.total_tiles;
   const int per = p.tiles_x * p.tiles_y;
   const int b = t / per, rem = t - b * per;
@@ -110,13 +118,15 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sW = sA + P_STAGES * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 9 * p.ncc * p.half_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (p.resident ? 9 * p.ncc * p.half_bytes : p.b_stages * p.b_stage_bytes));
   uint64_t* wfull = bars;                  // (the leader's is used)
   uint64_t* fullA = wfull + 1;             // (the leader's)
   uint64_t* emptyA = fullA + P_STAGES;     // each CTA's own
   uint64_t* tfull = emptyA + P_STAGES;     // each CTA's own
   uint64_t* tempty = tfull + P_ACC;        // (the leader's: both CTAs' epilogues arrive)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + P_ACC);
+  uint64_t* fullB = tempty + P_ACC;        // (the leader's)
+  uint64_t* emptyB = fullB + P_MAX_B;      // each CTA's own
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(emptyB + P_MAX_B);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,6 +140,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(wfull, 1);
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int a = 0; a < P_ACC; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 8); }
+    for (int s = 0; s < P_MAX_B; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc2(tmem_slot, 512);
@@ -143,18 +154,32 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
-      if (leader) mbar_expect_tx(wfull, 2u * 9u * static_cast<uint32_t>(p.ncc) * static_cast<uint32_t>(p.half_bytes));
-      for (int s = 0; s < 9 * p.ncc; ++s)
-        tma_load_2d_pair(sW + s * p.half_bytes, &tmW, wfull, 0, s * p.rows + static_cast<int>(rank) * p.half_rows);
-      int sa = 0;
-      uint32_t pha = 0;
+      if (p.resident) {
+        if (leader) mbar_expect_tx(wfull, 2u * 9u * static_cast<uint32_t>(p.ncc) * static_cast<uint32_t>(p.half_bytes));
+        for (int s = 0; s < 9 * p.ncc; ++s)
+          tma_load_2d_pair(sW + s * p.half_bytes, &tmW, wfull, 0, s * p.rows_total + static_cast<int>(rank) * p.half_rows);
+      }
+      int sa = 0, sb = 0, g = 0;
+      uint32_t pha = 0, phb = 0;
       for (int it = pair; it < p.items; it += n_pairs) {
-        const PTile tc = p_tile(p, 2 * it + static_cast<int>(rank));
+        const PTile tc = p_tile(p, it, static_cast<int>(rank));
         for (int cc = 0; cc < p.ncc; ++cc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           if (leader) mbar_expect_tx(&fullA[sa], 2u * p.a_tx);
           tma_load_4d_pair(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
           if (++sa == P_STAGES) { sa = 0; pha ^= 1; }
+          if (!p.resident) {
+            // this CTA's half of the nine (tap, chunk) slices, P_G to a ring stage, in the order the issuer consumes them
+            for (int t9 = 0; t9 < 9; ++t9) {
+              if (g == 0) {
+                mbar_wait(&emptyB[sb], phb ^ 1);
+                if (leader) mbar_expect_tx(&fullB[sb], 2u * P_G * static_cast<uint32_t>(p.half_bytes));
+              }
+              tma_load_2d_pair(sW + sb * p.b_stage_bytes + g * p.half_bytes, &tmW, &fullB[sb], 0,
+                               (t9 * p.ncc + cc) * p.rows_total + tc.n0 + static_cast<int>(rank) * p.half_rows);
+              if (++g == P_G) { g = 0; if (++sb == p.b_stages) { sb = 0; phb ^= 1; } }
+            }
+          }
         }
       }
     }
@@ -174,26 +199,49 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(((tap / 3) * P_TWP + (tap % 3)) * 128) >> 4;
       const int ncc = p.ncc, nk_last = p.nk_last;
-      mbar_wait(wfull, 0);
-      tc_fence_after();
-      int sa = 0, as = 0;
-      uint32_t pha = 0, aph = 0;
+      if (p.resident) { mbar_wait(wfull, 0); tc_fence_after(); }
+      const bool resident = p.resident != 0;
+      const uint32_t b_stage_step = static_cast<uint32_t>(p.b_stage_bytes) >> 4;
+      const int b_stages = p.b_stages, n_acc = p.n_acc;
+      int sa = 0, as = 0, sb = 0, g = 0;
+      uint32_t pha = 0, aph = 0, phb = 0;
       int li = 0;
       for (int it = pair; it < p.items; it += n_pairs, ++li) {
         if (p.dual && (li & 1) != iw) {
           // the other issuer's item: step the rings past it
           for (int cc = 0; cc < ncc; ++cc)
             if (++sa == P_STAGES) { sa = 0; pha ^= 1; }
-          if (++as == P_ACC) { as = 0; aph ^= 1; }
+          if (++as == n_acc) { as = 0; aph ^= 1; }
           continue;
         }
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * P_ACC_STRIDE;
+        const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         for (int cc = 0; cc < ncc; ++cc) {
           mbar_wait(&fullA[sa], pha);
           tc_fence_after();
-          if (issuer) {
+          if (!resident) {
+            const int nk = (cc == ncc - 1) ? nk_last : 4;
+            const uint32_t a_lo = a_lo0 + sa * a_step;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              if (g == 0) { mbar_wait(&fullB[sb], phb); tc_fence_after(); }
+              if (issuer) {
+                const uint32_t at = a_lo + tap_off[t9];
+                const uint32_t bl = w_lo0 + sb * b_stage_step + g * w_step;
+                umma2_f16_lo(d_tmem, at, bl, dhi, idesc, (cc | t9) != 0);
+                if (nk > 1) umma2_f16_lo(d_tmem, at + 2, bl + 2, dhi, idesc, 1);
+                if (nk > 2) umma2_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc, 1);
+                if (nk > 3) umma2_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc, 1);
+              }
+              if (++g == P_G) {
+                if (issuer) umma2_commit_mcast(&emptyB[sb], 0b11);     // both CTAs' halves of the stage are consumed
+                g = 0;
+                if (++sb == b_stages) { sb = 0; phb ^= 1; }
+              }
+            }
+            if (issuer) umma2_commit_mcast(&emptyA[sa], 0b11);
+          } else if (issuer) {
             const int nk = (cc == ncc - 1) ? nk_last : 4;     // pad lanes of the last chunk are zero: skip them
             const uint32_t a_lo = a_lo0 + sa * a_step;
 #pragma unroll
@@ -212,7 +260,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (issuer) umma2_commit_mcast(&tfull[as], 0b11);   // both CTAs' accumulators are complete
         __syncwarp();
-        if (++as == P_ACC) { as = 0; aph ^= 1; }
+        if (++as == n_acc) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp < P_MMA2_WARP) {
@@ -225,14 +273,14 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int li = 0;
     for (int it = pair; it < p.items; it += n_pairs, ++li) {
       if ((li & 1) != grp) continue;
-      const int as = li % P_ACC;
-      const uint32_t aph = static_cast<uint32_t>(li / P_ACC) & 1u;
-      const PTile tc = p_tile(p, 2 * it + static_cast<int>(rank));
+      const int as = li % p.n_acc;
+      const uint32_t aph = static_cast<uint32_t>(li / p.n_acc) & 1u;
+      const PTile tc = p_tile(p, it, static_cast<int>(rank));
       const int y = tc.y0 + r, x = tc.x0 + xx;
       const bool valid = tc.real && xx < P_TW && y < p.H && x < p.W;
       const size_t pix = (static_cast<size_t>(tc.real ? tc.b : 0) * p.H + (valid ? y : 0)) * p.W + (valid ? x : 0);
-      const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad : nullptr;
-      __half* yrow = p.y + pix * p.Cout_pad;
+      const __half* rrow = (p.res && valid) ? p.res + pix * p.Cout_pad + tc.n0 : nullptr;
+      __half* yrow = p.y + pix * p.Cout_pad + tc.n0;
       uint4 rnext[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
@@ -242,7 +290,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + as * P_ACC_STRIDE + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t taddr = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
       const int real_groups = p.rows >> 5;                  // Cout rows are a multiple of 32: a 32-column group is all real or all pad
       for (int g = 0; g < real_groups; ++g) {
         uint4 rq[4];
@@ -266,8 +314,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int q = 0; q < 4; ++q) {
           const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
           float4 b0, b1;                                     // bias of channels g*32 + q*8 .. + 8 (explicit ld.shared: 2 instead of 8 loads)
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_u + (g * 32 + q * 8) * 4));
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_u + (g * 32 + q * 8 + 4) * 4));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0.x), "=f"(b0.y), "=f"(b0.z), "=f"(b0.w) : "r"(bias_u + (tc.n0 + g * 32 + q * 8) * 4));
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b1.x), "=f"(b1.y), "=f"(b1.z), "=f"(b1.w) : "r"(bias_u + (tc.n0 + g * 32 + q * 8 + 4) * 4));
           const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -285,7 +333,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stg_v8(yrow + g * 32 + 16, o + 8);
         }
       }
-      if (valid) {
+      if (valid && p.n_tiles == 1) {
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};        // pad channels stay zero
         for (int c = p.rows; c < p.Cout_pad; c += 16) stg_v8(yrow + c, z);
       }
@@ -302,12 +350,12 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // CAL_E_UNSUPPORTED (no error set): the shape is served by conv3x3.cu
 int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
-  static const bool enabled = [] { const char* e = getenv("CAL_CONV_PAIR"); return !(e && e[0] == '0'); }();
+  static const int enabled = [] { const char* e = getenv("CAL_CONV_PAIR"); return e ? atoi(e) : 3; }();   // bit 0: resident halves, bit 1: streamed halves
   if (!enabled || a->ksize != 3 || a->stride != 1 || a->mode != 0 || !a->w_slices) return CAL_E_UNSUPPORTED;
-  if (a->Cout_rows % 32 != 0 || a->Cout_rows > 256 || a->Cout_rows < 32 || a->Cout_pad > 256) return CAL_E_UNSUPPORTED;
+  if (a->Cout_rows % 32 != 0 || a->Cout_rows < 64 || a->Cout_pad > 1024) return CAL_E_UNSUPPORTED;
   PairParams p{};
   p.B = a->B; p.H = a->Hout; p.W = a->Wout; p.Cout_pad = a->Cout_pad;
-  p.rows = a->Cout_rows; p.half_rows = a->Cout_rows / 2;
+  p.rows_total = a->Cout_rows;
   p.ncc = a->Cin_pad / 64;
   {
     const int cin = (a->Cin > 0 && a->Cin <= a->Cin_pad) ? a->Cin : a->Cin_pad;
@@ -315,20 +363,52 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
     if (p.nk_last < 1) p.nk_last = 1;
     if (p.nk_last > 4) p.nk_last = 4;
   }
-  p.half_bytes = p.half_rows * 128;
-  if (p.half_bytes % 1024 != 0) return CAL_E_UNSUPPORTED;           // slices stay on swizzle-atom boundaries
   p.a_stage_bytes = (P_R + 2) * P_TWP * 128 + 1024;                 // + pad rows read by the last taps of halo columns
   p.a_tx = static_cast<uint32_t>((P_R + 2) * P_TWP * 128);
+  const size_t tail = 64 * 8 + 32 + static_cast<size_t>(a->Cout_pad) * 4;
+  const size_t avail = static_cast<size_t>(227 * 1024 - smem_headroom());
+  const size_t fixed = 1024 + static_cast<size_t>(P_STAGES) * p.a_stage_bytes + tail;
+  // N tile: the whole Cout when it fits one MMA (and a double-buffered accumulator), else its widest divisor
+  p.n_tiles = 1;
+  while (a->Cout_rows % p.n_tiles != 0 || a->Cout_rows / p.n_tiles > 256 || (a->Cout_rows / p.n_tiles) % 32 != 0) {
+    if (++p.n_tiles > 8) return CAL_E_UNSUPPORTED;
+  }
+  if (p.n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;
+  p.rows = a->Cout_rows / p.n_tiles;
+  p.half_rows = p.rows / 2;
+  p.half_bytes = p.half_rows * 128;
+  if (p.half_bytes % 1024 != 0) return CAL_E_UNSUPPORTED;           // slices stay on swizzle-atom boundaries
+  p.acc_stride = (p.rows + 31) & ~31;
+  p.n_acc = 512 / p.acc_stride;
+  if (p.n_acc > P_ACC) p.n_acc = P_ACC;
+  if (p.n_acc < 2) return CAL_E_UNSUPPORTED;
+  p.n_acc &= ~1;                                                     // stage parity == epilogue group
   const size_t w_all = static_cast<size_t>(9) * p.ncc * p.half_bytes;
-  const size_t smem = 1024 + static_cast<size_t>(P_STAGES) * p.a_stage_bytes + w_all + 32 * 8 + 32 + static_cast<size_t>(a->Cout_pad) * 4;
   // worth a pair only where one CTA cannot hold the weights (those layers run with resident weights in conv3x3.cu)
-  if (smem > static_cast<size_t>(227 * 1024 - smem_headroom()) || 2 * w_all + 2 * p.a_stage_bytes <= 200 * 1024) return CAL_E_UNSUPPORTED;
+  if (p.n_tiles == 1 && 2 * w_all + 2 * static_cast<size_t>(p.a_stage_bytes) <= 200 * 1024) return CAL_E_UNSUPPORTED;
+  size_t smem;
+  if (p.n_tiles == 1 && fixed + w_all <= avail) {
+    if (!(enabled & 1)) return CAL_E_UNSUPPORTED;
+    p.resident = 1;
+    p.b_stages = 0; p.b_stage_bytes = 0;
+    smem = fixed + w_all;
+  } else {
+    if (!(enabled & 2)) return CAL_E_UNSUPPORTED;
+    p.resident = 0;
+    p.b_stage_bytes = P_G * p.half_bytes;
+    if (fixed >= avail) return CAL_E_UNSUPPORTED;
+    p.b_stages = static_cast<int>((avail - fixed) / p.b_stage_bytes);
+    if (p.b_stages > P_MAX_B) p.b_stages = P_MAX_B;
+    if (p.b_stages < 2) return CAL_E_UNSUPPORTED;
+    smem = fixed + static_cast<size_t>(p.b_stages) * p.b_stage_bytes;
+  }
   p.tiles_x = (a->Wout + P_TW - 1) / P_TW;
   p.tiles_y = (a->Hout + P_R - 1) / P_R;
   p.total_tiles = a->B * p.tiles_x * p.tiles_y;
-  p.items = (p.total_tiles + 1) / 2;
+  p.items = (p.total_tiles + 1) / 2 * p.n_tiles;
   p.relu = a->relu;
-  { static const bool du = [] { const char* e = getenv("CAL_PAIR_DUAL"); return !(e && e[0] == '0'); }(); p.dual = (du && 2 * p.ncc <= P_STAGES) ? 1 : 0; }
+  { static const bool du = [] { const char* e = getenv("CAL_PAIR_DUAL"); return !(e && e[0] == '0'); }();
+    p.dual = (du && p.resident && 2 * p.ncc <= P_STAGES && p.n_acc >= 2) ? 1 : 0; }
   p.bias = a->bias;
   p.res = reinterpret_cast<const __half*>(a->res);
   p.y = reinterpret_cast<__half*>(a->y);
@@ -342,7 +422,7 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
     if (rc != CAL_OK) return rc;
   }
   {
-    const uint64_t dims[2] = {64ull, 9ull * p.ncc * (uint64_t)a->Cout_rows};
+    const uint64_t dims[2] = {64ull, 9ull * p.ncc * (uint64_t)a->Cout_rows};   // slice-major: slice s = rows [s * Cout_rows, ...)
     const uint64_t strides[1] = {128ull};
     const uint32_t box[2] = {64, (uint32_t)p.half_rows};
     const int rc = encode_tmap_f16(&tmW, a->w, 2, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -354,6 +434,12 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
     CAL_CHECK_CUDA(cudaGetDevice(&dev));
     CAL_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
     CAL_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  {
+    static const bool show = getenv("CAL_DEBUG_CONFIG") != nullptr;
+    if (show)
+      fprintf(stderr, "pair conv %dx%d Cin_pad %d Cout %d: N tile %d x %d resident %d b_stages %d n_acc %d smem %zu items %d dual %d\n", a->Hout,
+              a->Wout, a->Cin_pad, a->Cout_rows, p.rows, p.n_tiles, p.resident, p.b_stages, p.n_acc, smem, p.items, p.dual);
   }
   int grid = 2 * p.items < num_sms ? 2 * p.items : (num_sms & ~1);
   cudaLaunchConfig_t cfg{};

@@ -2,7 +2,7 @@
 so that one `ncu --set full --nvtx --nvtx-include "cap/"` run captures exactly these:
   BasicBlock 48 @135x240 in one kernel (basicblock_kernel<3,0>),
   3x3 48->48 @135x240 without / with residual (conv3x3_halo_kernel<1,2> / <1,1>),
-  3x3 96->96 @68x120, 192->192 @34x60, 384->384 @17x30 (<0,2> / <0,1>), 1x1 64->256 @135x240 (conv_tc).
+  3x3 96->96 @68x120, 192->192 @34x60, 384->384 @17x30 (conv3x3_pair_kernel), 1x1 64->256 @135x240 (conv_tc).
 python tools/ncu_shapes.py [B] [first n shapes]"""
 import os
 import sys
@@ -42,6 +42,8 @@ for ks, cin, cout, h, w, res in SHAPES[:LIMIT]:
     x = torch.randn(B, h, w, cp, device="cuda").half()
     x[..., cin:] = 0
     wt = (torch.randn(rows, ks * ks * cp, device="cuda") / 30).half()
+    if ks == 3:       # slice-major, as the engine packs the 3x3 stride-1 weights (the CTA-pair kernel takes only these)
+        wt = wt.reshape(rows, ks * ks * cp // 64, 64).permute(1, 0, 2).contiguous()
     bias = torch.zeros(op, device="cuda")
     y = torch.empty(B, h, w, op, device="cuda", dtype=torch.half)
     r = torch.randn_like(y) if res else None
@@ -51,7 +53,7 @@ for ks, cin, cout, h, w, res in SHAPES[:LIMIT]:
             torch.cuda.synchronize()
             torch.cuda.nvtx.range_push("cap")
             e0.record()
-        ops.conv2d(x, wt, bias, y, ksize=ks, stride=1, cout_rows=rows, relu=True, res=r, cin=cin)
+        ops.conv2d(x, wt, bias, y, ksize=ks, stride=1, cout_rows=rows, relu=True, res=r, cin=cin, w_slices=(ks == 3))
     e1.record()
     torch.cuda.synchronize()
     torch.cuda.nvtx.range_pop()

@@ -1,4 +1,4 @@
-// conv3x3_pair.cu - 3x3 stride-1 convolution (+folded BN)(+residual)(+ReLU) on CTA PAIRS (tcgen05 cta_group::2)
+// conv3x3_pair.cu - 3x3 convolution, stride 1 or 2 (+folded BN)(+residual)(+ReLU) on CTA PAIRS (tcgen05 cta_group::2)
 // for the layers whose weights do not fit one CTA's shared memory but whose HALF does: C = 96 at H/8 x W/8
 // (128 launches a step).  In conv3x3.cu those layers stream their weights through a ring and spend as long in
 // the ring's barrier hand-overs as in MMAs.  Here:
@@ -23,9 +23,8 @@ namespace {
 
 constexpr int P_THREADS = 352;            // warp 0 TMA producer, warps 1 and 10 MMA issuers (leader CTA), warps 2..9 epilogue
 constexpr int P_MMA2_WARP = 10;
-constexpr int P_STAGES = 4;               // input patch ring
+constexpr int P_STAGES = 4;               // input patch ring (at most; stride 2: two stages of four phase patches)
 constexpr int P_ACC = 4;                  // accumulator stages in TMEM at most (512 columns / N tile)
-constexpr int P_G = 3;                    // weight slices per ring stage (streamed mode): one barrier pair per stage
 constexpr int P_MAX_B = 6;
 constexpr int P_TWP = 32, P_TW = 30, P_R = 4;
 constexpr uint32_t P_PEER_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's leader CTA
@@ -35,7 +34,10 @@ struct PairParams {
   int tiles_x, tiles_y, total_tiles, items;
   int rows, half_rows, ncc, nk_last;   // rows = N of an MMA (the N tile); half_rows of every slice live in each CTA
   int rows_total, n_tiles;             // weight rows per slice in the tensor; N tiles (Cout = n_tiles * rows)
-  int resident;                        // all half-slices resident, or streamed through a ring of `b_stages` stages of P_G slices
+  int resident;                        // all half-slices resident, or streamed through a ring of `b_stages` stages of G slices
+  int G;                               // weight slices per ring stage (3 or 1): one barrier pair per stage
+  int stride;                          // 1, or 2: the patch is loaded as its four (row, column) parity phases
+  int a_stages, phase_bytes;
   int b_stages, b_stage_bytes, n_acc, acc_stride;
   int relu;
   int dual;                // second MMA-issuing warp (alternate items); needs 2 * ncc <= P_STAGES: a parity wait is only meaningful within one pass of the ring
@@ -117,7 +119,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
-  uint8_t* sW = sA + P_STAGES * p.a_stage_bytes;
+  uint8_t* sW = sA + p.a_stages * p.a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + (p.resident ? 9 * p.ncc * p.half_bytes : p.b_stages * p.b_stage_bytes));
   uint64_t* wfull = bars;                  // (the leader's is used)
   uint64_t* fullA = wfull + 1;             // (the leader's)
@@ -166,18 +168,27 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int cc = 0; cc < p.ncc; ++cc) {
           mbar_wait(&emptyA[sa], pha ^ 1);
           if (leader) mbar_expect_tx(&fullA[sa], 2u * p.a_tx);
-          tma_load_4d_pair(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
-          if (++sa == P_STAGES) { sa = 0; pha ^= 1; }
+          if (p.stride == 1) {
+            tma_load_4d_pair(sA + sa * p.a_stage_bytes, &tmA, &fullA[sa], cc * 64, tc.x0 - 1, tc.y0 - 1, tc.b);
+          } else {
+            // stride 2: the four (row parity, column parity) phases of the input patch, each a dense 5 x 32-pixel tile
+            // (tensor-map element strides of 2); phase 1 = odd rows / columns starts one input pixel before the tile
+#pragma unroll
+            for (int ph4 = 0; ph4 < 4; ++ph4)
+              tma_load_4d_pair(sA + sa * p.a_stage_bytes + ph4 * p.phase_bytes, &tmA, &fullA[sa], cc * 64,
+                               2 * tc.x0 - (ph4 & 1), 2 * tc.y0 - (ph4 >> 1), tc.b);
+          }
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           if (!p.resident) {
-            // this CTA's half of the nine (tap, chunk) slices, P_G to a ring stage, in the order the issuer consumes them
+            // this CTA's half of the nine (tap, chunk) slices, p.G to a ring stage, in the order the issuer consumes them
             for (int t9 = 0; t9 < 9; ++t9) {
               if (g == 0) {
                 mbar_wait(&emptyB[sb], phb ^ 1);
-                if (leader) mbar_expect_tx(&fullB[sb], 2u * P_G * static_cast<uint32_t>(p.half_bytes));
+                if (leader) mbar_expect_tx(&fullB[sb], 2u * static_cast<uint32_t>(p.G) * static_cast<uint32_t>(p.half_bytes));
               }
               tma_load_2d_pair(sW + sb * p.b_stage_bytes + g * p.half_bytes, &tmW, &fullB[sb], 0,
                                (t9 * p.ncc + cc) * p.rows_total + tc.n0 + static_cast<int>(rank) * p.half_rows);
-              if (++g == P_G) { g = 0; if (++sb == p.b_stages) { sb = 0; phb ^= 1; } }
+              if (++g == p.G) { g = 0; if (++sb == p.b_stages) { sb = 0; phb ^= 1; } }
             }
           }
         }
@@ -197,7 +208,16 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t w_lo0 = dlo + ((smem_u32(sW) & 0x3FFFF) >> 4), w_step = static_cast<uint32_t>(p.half_bytes) >> 4;
       uint32_t tap_off[9];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) tap_off[tap] = static_cast<uint32_t>(((tap / 3) * P_TWP + (tap % 3)) * 128) >> 4;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap % 3;
+        if (p.stride == 1) {
+          tap_off[tap] = static_cast<uint32_t>((dy * P_TWP + dx) * 128) >> 4;
+        } else {
+          // input row 2 y - 1 + dy: dy = 1 is row y of the even phase, dy = 0 / 2 rows y / y + 1 of the odd phase
+          const int phase = (dy != 1 ? 2 : 0) + (dx != 1 ? 1 : 0);
+          tap_off[tap] = static_cast<uint32_t>(phase * p.phase_bytes + ((dy == 2 ? P_TWP : 0) + (dx == 2 ? 1 : 0)) * 128) >> 4;
+        }
+      }
       const int ncc = p.ncc, nk_last = p.nk_last;
       if (p.resident) { mbar_wait(wfull, 0); tc_fence_after(); }
       const bool resident = p.resident != 0;
@@ -210,7 +230,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (p.dual && (li & 1) != iw) {
           // the other issuer's item: step the rings past it
           for (int cc = 0; cc < ncc; ++cc)
-            if (++sa == P_STAGES) { sa = 0; pha ^= 1; }
+            if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
           if (++as == n_acc) { as = 0; aph ^= 1; }
           continue;
         }
@@ -234,7 +254,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (nk > 2) umma2_f16_lo(d_tmem, at + 4, bl + 4, dhi, idesc, 1);
                 if (nk > 3) umma2_f16_lo(d_tmem, at + 6, bl + 6, dhi, idesc, 1);
               }
-              if (++g == P_G) {
+              if (++g == p.G) {
                 if (issuer) umma2_commit_mcast(&emptyB[sb], 0b11);     // both CTAs' halves of the stage are consumed
                 g = 0;
                 if (++sb == b_stages) { sb = 0; phb ^= 1; }
@@ -256,7 +276,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             umma2_commit_mcast(&emptyA[sa], 0b11);          // both CTAs' patches are consumed
           }
           __syncwarp();
-          if (++sa == P_STAGES) { sa = 0; pha ^= 1; }
+          if (++sa == p.a_stages) { sa = 0; pha ^= 1; }
         }
         if (issuer) umma2_commit_mcast(&tfull[as], 0b11);   // both CTAs' accumulators are complete
         __syncwarp();
@@ -291,7 +311,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * p.acc_stride + (static_cast<uint32_t>(quarter * 32) << 16);
-      const int real_groups = p.rows >> 5;                  // Cout rows are a multiple of 32: a 32-column group is all real or all pad
+      const int real_groups = p.rows >> 5;                  // 32-column groups of real channels (+ one 16-column group when Cout % 32 == 16)
+      const bool tail16 = (p.rows & 16) != 0;
       for (int g = 0; g < real_groups; ++g) {
         uint4 rq[4];
 #pragma unroll
@@ -303,7 +324,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t acc[32];
         tmem_ld32(taddr + g * 32, acc);
         tmem_ld_wait();
-        if (g + 1 == real_groups) {
+        if (g + 1 == real_groups && !tail16) {
           // the last columns are in registers: hand the accumulator stage back to the leader's issuer
           tc_fence_before();
           __syncwarp();
@@ -333,6 +354,36 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           stg_v8(yrow + g * 32 + 16, o + 8);
         }
       }
+      if (tail16) {
+        // a trailing 16-channel group (Cout = 48: N = 48)
+        const int c0 = real_groups * 32;
+        uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+        if (rrow) { r0 = ldg_nc_v4(rrow + c0); r1 = ldg_nc_v4(rrow + c0 + 8); }
+        uint32_t acc[16];
+        tmem_ld16(taddr + c0, acc);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty[as]);
+        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 bq;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(bq.x), "=f"(bq.y), "=f"(bq.z), "=f"(bq.w) : "r"(bias_u + (tc.n0 + c0 + q * 4) * 4));
+          const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int c = q * 4 + 2 * j;
+            const __half2 rh = *reinterpret_cast<const __half2*>(&rr[q * 2 + j]);
+            float a = __uint_as_float(acc[c]) + (bv[2 * j] + __low2float(rh));
+            float b2 = __uint_as_float(acc[c + 1]) + (bv[2 * j + 1] + __high2float(rh));
+            if (p.relu) { a = fmaxf(a, 0.0f); b2 = fmaxf(b2, 0.0f); }
+            o[q * 2 + j] = p_pack_half2(a, b2);
+          }
+        }
+        if (valid) stg_v8(yrow + c0, o);
+      }
       if (valid && p.n_tiles == 1) {
         const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};        // pad channels stay zero
         for (int c = p.rows; c < p.Cout_pad; c += 16) stg_v8(yrow + c, z);
@@ -350,30 +401,42 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 // CAL_E_UNSUPPORTED (no error set): the shape is served by conv3x3.cu
 int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
-  static const int enabled = [] { const char* e = getenv("CAL_CONV_PAIR"); return e ? atoi(e) : 3; }();   // bit 0: resident halves, bit 1: streamed halves
-  if (!enabled || a->ksize != 3 || a->stride != 1 || a->mode != 0 || !a->w_slices) return CAL_E_UNSUPPORTED;
-  if (a->Cout_rows % 32 != 0 || a->Cout_rows < 64 || a->Cout_pad > 1024) return CAL_E_UNSUPPORTED;
+  // bit 0: stride 1 with resident halves, bit 1: stride 1 with streamed halves, bit 2: stride 2
+  static const int enabled = [] { const char* e = getenv("CAL_CONV_PAIR"); return e ? atoi(e) : 7; }();
+  if (!enabled || a->ksize != 3 || (a->stride != 1 && a->stride != 2) || a->mode != 0 || !a->w_slices) return CAL_E_UNSUPPORTED;
+  if (a->stride == 2 && !(enabled & 4)) return CAL_E_UNSUPPORTED;
+  if (a->Cout_rows % 16 != 0 || a->Cout_rows < 32 || a->Cout_pad > 1024) return CAL_E_UNSUPPORTED;
   PairParams p{};
   p.B = a->B; p.H = a->Hout; p.W = a->Wout; p.Cout_pad = a->Cout_pad;
   p.rows_total = a->Cout_rows;
   p.ncc = a->Cin_pad / 64;
+  p.stride = a->stride;
   {
     const int cin = (a->Cin > 0 && a->Cin <= a->Cin_pad) ? a->Cin : a->Cin_pad;
     p.nk_last = (cin - (p.ncc - 1) * 64 + 15) / 16;
     if (p.nk_last < 1) p.nk_last = 1;
     if (p.nk_last > 4) p.nk_last = 4;
   }
-  p.a_stage_bytes = (P_R + 2) * P_TWP * 128 + 1024;                 // + pad rows read by the last taps of halo columns
-  p.a_tx = static_cast<uint32_t>((P_R + 2) * P_TWP * 128);
+  if (a->stride == 1) {
+    p.phase_bytes = 0;
+    p.a_stage_bytes = (P_R + 2) * P_TWP * 128 + 1024;               // + pad rows read by the last taps of halo columns
+    p.a_tx = static_cast<uint32_t>((P_R + 2) * P_TWP * 128);
+    p.a_stages = P_STAGES;
+  } else {
+    p.phase_bytes = (P_R + 1) * P_TWP * 128;                        // one parity phase of the patch: 5 rows x 32 pixels
+    p.a_stage_bytes = 4 * p.phase_bytes + 1024;
+    p.a_tx = static_cast<uint32_t>(4 * p.phase_bytes);
+    p.a_stages = 2;
+  }
   const size_t tail = 64 * 8 + 32 + static_cast<size_t>(a->Cout_pad) * 4;
   const size_t avail = static_cast<size_t>(227 * 1024 - smem_headroom());
-  const size_t fixed = 1024 + static_cast<size_t>(P_STAGES) * p.a_stage_bytes + tail;
+  const size_t fixed = 1024 + static_cast<size_t>(p.a_stages) * p.a_stage_bytes + tail;
   // N tile: the whole Cout when it fits one MMA (and a double-buffered accumulator), else its widest divisor
   p.n_tiles = 1;
-  while (a->Cout_rows % p.n_tiles != 0 || a->Cout_rows / p.n_tiles > 256 || (a->Cout_rows / p.n_tiles) % 32 != 0) {
+  while (a->Cout_rows % p.n_tiles != 0 || a->Cout_rows / p.n_tiles > 256 || (a->Cout_rows / p.n_tiles) % 16 != 0) {
     if (++p.n_tiles > 8) return CAL_E_UNSUPPORTED;
   }
-  if (p.n_tiles > 1 && a->Cout_rows != a->Cout_pad) return CAL_E_UNSUPPORTED;
+  if (p.n_tiles > 1 && (a->Cout_rows != a->Cout_pad || (a->Cout_rows / p.n_tiles) % 32 != 0)) return CAL_E_UNSUPPORTED;
   p.rows = a->Cout_rows / p.n_tiles;
   p.half_rows = p.rows / 2;
   p.half_bytes = p.half_rows * 128;
@@ -384,19 +447,23 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
   if (p.n_acc < 2) return CAL_E_UNSUPPORTED;
   p.n_acc &= ~1;                                                     // stage parity == epilogue group
   const size_t w_all = static_cast<size_t>(9) * p.ncc * p.half_bytes;
-  // worth a pair only where one CTA cannot hold the weights (those layers run with resident weights in conv3x3.cu)
-  if (p.n_tiles == 1 && 2 * w_all + 2 * static_cast<size_t>(p.a_stage_bytes) <= 200 * 1024) return CAL_E_UNSUPPORTED;
+  // stride 1: worth a pair only where one CTA cannot hold the weights (those layers run with resident weights in
+  // conv3x3.cu); stride 2: always - the generic kernel fetches every patch nine times (once per tap) and runs at
+  // the L2 -> SM cap, the four parity phases here are 80 KB instead of 144 KB per tile and chunk
+  if (a->stride == 1 && p.n_tiles == 1 && 2 * w_all + 2 * static_cast<size_t>(p.a_stage_bytes) <= 200 * 1024) return CAL_E_UNSUPPORTED;
   size_t smem;
+  p.G = 3;
   if (p.n_tiles == 1 && fixed + w_all <= avail) {
-    if (!(enabled & 1)) return CAL_E_UNSUPPORTED;
+    if (a->stride == 1 && !(enabled & 1)) return CAL_E_UNSUPPORTED;
     p.resident = 1;
     p.b_stages = 0; p.b_stage_bytes = 0;
     smem = fixed + w_all;
   } else {
-    if (!(enabled & 2)) return CAL_E_UNSUPPORTED;
-    p.resident = 0;
-    p.b_stage_bytes = P_G * p.half_bytes;
+    if (a->stride == 1 && !(enabled & 2)) return CAL_E_UNSUPPORTED;
     if (fixed >= avail) return CAL_E_UNSUPPORTED;
+    p.resident = 0;
+    if ((avail - fixed) / (3 * static_cast<size_t>(p.half_bytes)) < 2) p.G = 1;       // wide slices next to the stride-2 patches: one per stage
+    p.b_stage_bytes = p.G * p.half_bytes;
     p.b_stages = static_cast<int>((avail - fixed) / p.b_stage_bytes);
     if (p.b_stages > P_MAX_B) p.b_stages = P_MAX_B;
     if (p.b_stages < 2) return CAL_E_UNSUPPORTED;
@@ -408,7 +475,7 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
   p.items = (p.total_tiles + 1) / 2 * p.n_tiles;
   p.relu = a->relu;
   { static const bool du = [] { const char* e = getenv("CAL_PAIR_DUAL"); return !(e && e[0] == '0'); }();
-    p.dual = (du && p.resident && 2 * p.ncc <= P_STAGES && p.n_acc >= 2) ? 1 : 0; }
+    p.dual = (du && p.resident && 2 * p.ncc <= p.a_stages && p.n_acc >= 2) ? 1 : 0; }
   p.bias = a->bias;
   p.res = reinterpret_cast<const __half*>(a->res);
   p.y = reinterpret_cast<__half*>(a->y);
@@ -417,8 +484,12 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
   {
     const uint64_t dims[4] = {(uint64_t)a->Cin_pad, (uint64_t)a->Win, (uint64_t)a->Hin, (uint64_t)a->B};
     const uint64_t strides[3] = {(uint64_t)a->Cin_pad * 2, (uint64_t)a->Win * a->Cin_pad * 2, (uint64_t)a->Hin * a->Win * a->Cin_pad * 2};
-    const uint32_t box[4] = {64, (uint32_t)P_TWP, (uint32_t)(P_R + 2), 1};
-    const int rc = encode_tmap_f16(&tmA, a->x, 4, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+    // stride 2: one parity phase per load - every second pixel of every second row (element strides), 32 x 5 of them
+    const uint32_t box1[4] = {64, (uint32_t)P_TWP, (uint32_t)(P_R + 2), 1};
+    const uint32_t box2[4] = {64, (uint32_t)(2 * P_TWP), (uint32_t)(2 * (P_R + 1)), 1};
+    const uint32_t es2[4] = {1, 2, 2, 1};
+    const int rc = encode_tmap_f16(&tmA, a->x, 4, dims, strides, a->stride == 1 ? box1 : box2, a->stride == 1 ? nullptr : es2,
+                                   CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != CAL_OK) return rc;
   }
   {
@@ -438,8 +509,8 @@ int launch_conv3x3_pair(const CalConvArgs* a, void* stream) {
   {
     static const bool show = getenv("CAL_DEBUG_CONFIG") != nullptr;
     if (show)
-      fprintf(stderr, "pair conv %dx%d Cin_pad %d Cout %d: N tile %d x %d resident %d b_stages %d n_acc %d smem %zu items %d dual %d\n", a->Hout,
-              a->Wout, a->Cin_pad, a->Cout_rows, p.rows, p.n_tiles, p.resident, p.b_stages, p.n_acc, smem, p.items, p.dual);
+      fprintf(stderr, "pair conv s%d %dx%d Cin_pad %d Cout %d: N tile %d x %d resident %d G %d b_stages %d n_acc %d smem %zu items %d dual %d\n", a->stride,
+              a->Hout, a->Wout, a->Cin_pad, a->Cout_rows, p.rows, p.n_tiles, p.resident, p.G, p.b_stages, p.n_acc, smem, p.items, p.dual);
   }
   int grid = 2 * p.items < num_sms ? 2 * p.items : (num_sms & ~1);
   cudaLaunchConfig_t cfg{};

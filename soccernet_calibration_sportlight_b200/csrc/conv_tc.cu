@@ -550,8 +550,15 @@ extern "C" int cal_conv2d(const CalConvArgs* a, void* stream) {
     CAL_REQUIRE(a->Cout_pad == 64 && a->n_classes >= 1 && a->n_classes <= a->Cout_rows && !a->res, CAL_E_UNSUPPORTED,
                 "cal_conv2d: softmax modes need Cout_pad == 64, n_classes <= Cout_rows, no residual");
 
-  CAL_REQUIRE(!a->w_slices || (a->ksize == 3 && a->stride == 1 && a->mode == 0), CAL_E_INVALID,
-              "cal_conv2d: slice-major weights are for 3x3 stride-1 convs");
+  CAL_REQUIRE(!a->w_slices || (a->ksize == 3 && a->mode == 0), CAL_E_INVALID, "cal_conv2d: slice-major weights are for 3x3 convs");
+  if (a->ksize == 3 && a->stride == 2 && a->w_slices) {
+    // stride-2 3x3 layers: CTA-pair kernel with parity-phase patches (conv3x3_pair.cu); the generic kernel below takes
+    // K-major weights
+    const int rcp = launch_conv3x3_pair(a, stream);
+    if (rcp != CAL_E_UNSUPPORTED) return rcp;
+    set_error("cal_conv2d: shape needs the generic kernel, which takes K-major weights");
+    return CAL_E_UNSUPPORTED;
+  }
   {
     // 3x3 stride-1 layers: halo-tile kernel (conv3x3.cu); CAL_CONV_HALO=0 forces the generic one
     static const bool use_halo = [] { const char* e = getenv("CAL_CONV_HALO"); return !(e && e[0] == '0'); }();

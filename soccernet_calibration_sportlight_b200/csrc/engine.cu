@@ -227,7 +227,7 @@ static int prepare(Net& n, const float* blob) {
     if (id == n.conv1 || id == n.head1 || id == n.head2) continue;
     Conv& c = n.convs[id];
     const Folded f = fold(c, blob);
-    const int rc = pack(n, c, f.w.data(), c.cout, c.cin, c.cin, 0, f.b.data(), 0, c.k == 3 && c.s == 1);
+    const int rc = pack(n, c, f.w.data(), c.cout, c.cin, c.cin, 0, f.b.data(), 0, c.k == 3);   // 3x3: slice-major (+ a K-major copy for the generic kernel)
     if (rc != CAL_OK) return rc;
   }
   {  // stem conv1: fp32 (64, 27) [co][ci*9 + ky*3 + kx]

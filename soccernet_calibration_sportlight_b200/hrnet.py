@@ -458,7 +458,7 @@ class HRNetHeatmap:
         p.cin_pad, p.cout_pad, p.k, p.s = packing.pad_to(w.shape[1]), bp.numel(), k, s
         p.cin = int(w.shape[1])
         # 3x3 stride-1 layers: slice-major weights (every (tap, 64-channel chunk) slice contiguous)
-        p.slices = bool(self.slice_major and k == 3 and s == 1)
+        p.slices = bool(self.slice_major and k == 3)
         p.w_k = p.w                       # K-major copy for the generic kernel (fallback shapes)
         if p.slices:
             p.w = p.w.reshape(p.rows, k * k * p.cin_pad // 64, 64).permute(1, 0, 2).contiguous()

@@ -37,13 +37,22 @@ def conv_case(B, H, W, ci, co, k, s, relu=True, res=False, mode=0, ncls=0, seed=
         ops.conv2d(xh, wp.to(dev), bp.to(dev), y, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16, cin=ci)
         got = packing.from_nhwc16(y, co)
         assert bool((y[..., co:] == 0).all()), "channel padding lanes must be written as zero"
-        if k == 3 and s == 1:
-            # slice-major weights (every (tap, chunk) slice contiguous) must give the same bits
+        if k == 3:
+            # slice-major weights (every (tap, chunk) slice contiguous; the halo / CTA-pair kernels) must give the same bits
             ws = wp.reshape(rows, -1, 64).permute(1, 0, 2).contiguous().to(dev)
             y2 = torch.full_like(y, float("nan"))
-            ops.conv2d(xh, ws, bp.to(dev), y2, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16, cin=ci,
-                       w_slices=True)
-            assert torch.equal(y, y2)
+            try:
+                ops.conv2d(xh, ws, bp.to(dev), y2, ksize=k, stride=s, cout_rows=rows, relu=relu, res=r16, cin=ci,
+                           w_slices=True)
+            except ops._lib.CalError as e:
+                assert s == 2 and "generic kernel" in str(e)      # a stride-2 shape only the K-major kernel serves
+            else:
+                if s == 2 and ci > 64:
+                    # the pair kernel accumulates chunk-major, the generic one tap-major: fp32 rounding, an fp16 ulp here and there
+                    assert float((y.float() - y2.float()).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+                    assert bool((y2[..., co:] == 0).all())
+                else:
+                    assert torch.equal(y, y2)
         tol = 2e-3 * max(1.0, float(ref.abs().max())) + 1e-3
     else:
         ref = F.log_softmax(ref, 1) if mode == 1 else F.softmax(ref, 1)
@@ -71,6 +80,9 @@ CONV_CASES = [
     dict(B=2, H=17, W=31, ci=48, co=96, k=3, s=2),
     dict(B=1, H=135, W=240, ci=256, co=96, k=3, s=2),
     dict(B=1, H=34, W=60, ci=192, co=384, k=3, s=2, res=True, relu=True),
+    dict(B=3, H=135, W=240, ci=48, co=48, k=3, s=2, res=True),
+    dict(B=2, H=67, W=121, ci=96, co=192, k=3, s=2),
+    dict(B=40, H=34, W=60, ci=48, co=96, k=3, s=2, res=True),
     dict(B=1, H=20, W=24, ci=384, co=48, k=1, s=1, relu=False),
     dict(B=1, H=20, W=24, ci=64, co=784, k=1, s=1, res=True),
     dict(B=1, H=20, W=24, ci=784, co=58, k=1, s=1, mode=1, ncls=58, scale=4.0),

@@ -265,6 +265,7 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
     // ---------------------------------------------------------------- epilogue of conv1: accumulator -> intermediate chunk
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;               // pixel of the chunk: row = quarter, column = lane
+    const uint32_t sMid_u = smem_u32(sMid), bias_u = smem_u32(s_bias);
     int slot = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int s = blockIdx.x; s < p.strips; s += gridDim.x) {
@@ -280,8 +281,8 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
         const uint32_t taddr = tmem_base + as * ACC + (static_cast<uint32_t>(quarter * 32) << 16);
         // the chunk's slot must have been read for the last time (conv2 three steps back)
         BB_WAIT(&midEmpty[slot], ph ^ 1, 1);
-        uint8_t* row = sMid + slot * BB_CH + m * 128;
-        uint8_t* mrow = sMid + BB_SLOTS * BB_CH + m * 128;
+        const uint32_t row = sMid_u + slot * BB_CH + m * 128;
+        const uint32_t mrow = sMid_u + BB_SLOTS * BB_CH + m * 128;
         const bool mirror = slot == 0 && m < BB_MIR_ROWS;
         bb_acc_blocks<NB, TAP3>(taddr, p.ablate, [&] {
           tc_fence_before();                                     // accumulator drained
@@ -289,10 +290,9 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
           if (lane == 0) mbar_arrive(&t1empty[as]);
         }, [&](int cb, const float (&v)[16]) {
           uint32_t o[8];
-          const float4* bb4 = reinterpret_cast<const float4*>(s_bias + cb * 16);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bq = bb4[j4];
+            const float4 bq = lds_v4f(bias_u + (cb * 16 + j4 * 4) * 4);
             const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -305,11 +305,11 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
             }
           }
           const uint4 lo = make_uint4(o[0], o[1], o[2], o[3]), hi = make_uint4(o[4], o[5], o[6], o[7]);
-          *reinterpret_cast<uint4*>(row + (((2 * cb) ^ (m & 7)) << 4)) = lo;
-          *reinterpret_cast<uint4*>(row + (((2 * cb + 1) ^ (m & 7)) << 4)) = hi;
+          sts_v4(row + (((2 * cb) ^ (m & 7)) << 4), lo);
+          sts_v4(row + (((2 * cb + 1) ^ (m & 7)) << 4), hi);
           if (mirror) {
-            *reinterpret_cast<uint4*>(mrow + (((2 * cb) ^ (m & 7)) << 4)) = lo;
-            *reinterpret_cast<uint4*>(mrow + (((2 * cb + 1) ^ (m & 7)) << 4)) = hi;
+            sts_v4(mrow + (((2 * cb) ^ (m & 7)) << 4), lo);
+            sts_v4(mrow + (((2 * cb + 1) ^ (m & 7)) << 4), hi);
           }
         });
         fence_proxy_async();                          // chunk -> visible to the tensor core's shared-memory reads
@@ -323,6 +323,7 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- epilogue of conv2: + bias + block input, ReLU, store
     const int quarter = warp & 3;
+    const uint32_t bias_u = smem_u32(s_bias);
     int as = 0;
     uint32_t aph = 0;
     for (int s = blockIdx.x; s < p.strips; s += gridDim.x) {
@@ -354,10 +355,9 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
           uint32_t o[8];
           const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-          const float4* bb4 = reinterpret_cast<const float4*>(s_bias + 64 + cb * 16);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 bq = bb4[j4];
+            const float4 bq = lds_v4f(bias_u + (64 + cb * 16 + j4 * 4) * 4);
             const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {

@@ -146,6 +146,17 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   return r;
 }
 
+// explicit shared-memory accesses from 32-bit addresses: pointers that come out of integer arithmetic make the compiler
+// fall back to generic loads / stores with 64-bit address registers - an epilogue does a dozen of them per pixel
+__device__ __forceinline__ float4 lds_v4f(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane and instruction
 __device__ __forceinline__ void stg_v8(void* p, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),

@@ -447,6 +447,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int r = m / p.TWp, xx = m - r * p.TWp;
     const int ms = r * p.TW + xx;                            // row of this pixel in the dense R x TW staging tile
     const bool leader = (quarter == 2 && lane == 0);         // first warp of the group
+    const uint32_t bias_u = smem_u32(s_bias);
     uint8_t* sStage = sOut + grp * p.nblk * H_STAGE_BLOCK;
     const bool prefetch_res = !DX && (p.res != nullptr) && groups_total <= 2 && T <= 2;
     // residual rows are fetched one of this group's tiles ahead (the accumulator ring lets the
@@ -546,17 +547,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // which is what bounds them - each lane writes its pixel's 32 channels as two full sectors.
           if (!valid) return;
           uint32_t o[16];
+          const uint32_t bb_u = bias_u + (tc.n0 + g * 32) * 4;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+            const float4 b0 = lds_v4f(bb_u + q * 32), b1 = lds_v4f(bb_u + q * 32 + 16);
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int c = q * 8 + 2 * j;
               const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
               float a = (g * 32 + c < p.mma_n) ? __uint_as_float(acc[c]) : 0.0f;
               float b = (g * 32 + c + 1 < p.mma_n) ? __uint_as_float(acc[c + 1]) : 0.0f;
-              a += bb[c] + __low2float(rh);
-              b += bb[c + 1] + __high2float(rh);
+              a += bv[2 * j] + __low2float(rh);
+              b += bv[2 * j + 1] + __high2float(rh);
               if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
               o[q * 4 + j] = h_pack_half2(a, b);
             }
@@ -621,10 +625,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t o[8];
             const uint4 r0 = rdx[2 * cb], r1 = rdx[2 * cb + 1];
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            const float4* bb4 = reinterpret_cast<const float4*>(s_bias + tc.n0 + cb * 16);
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 bq = bb4[j4];
+              const float4 bq = lds_v4f(bias_u + (tc.n0 + cb * 16 + j4 * 4) * 4);
               const float bv[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
               for (int h2 = 0; h2 < 2; ++h2) {

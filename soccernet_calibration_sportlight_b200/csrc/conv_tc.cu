@@ -249,19 +249,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) acc[j] = 0u;
           }
           if (valid) {
-            const float* bb = s_bias + tc.n0 + g * 32;
+            const uint32_t bb_u = smem_u32(s_bias) + (tc.n0 + g * 32) * 4;
             uint32_t o[16];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t rr[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+              const float4 b0 = lds_v4f(bb_u + q * 32), b1 = lds_v4f(bb_u + q * 32 + 16);
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int c = q * 8 + 2 * j;
                 const __half2 rh = *reinterpret_cast<const __half2*>(&rr[j]);
                 float a = (g * 32 + c < p.mma_n) ? __uint_as_float(acc[c]) : 0.0f;
                 float b = (g * 32 + c + 1 < p.mma_n) ? __uint_as_float(acc[c + 1]) : 0.0f;
-                a += bb[c] + __low2float(rh);
-                b += bb[c + 1] + __high2float(rh);
+                a += bv[2 * j] + __low2float(rh);
+                b += bv[2 * j + 1] + __high2float(rh);
                 if (p.relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
                 o[q * 4 + j] = pack_half2(a, b);
               }

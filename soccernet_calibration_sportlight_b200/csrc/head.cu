@@ -539,6 +539,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_chain_kernel(const __grid_
       // ---------------------------------------------------------------- epilogue
       const int y = y0 + py, x = x0 + px;
       const bool valid = (y < p.H) && (x < p.W);
+      const uint32_t bias_u = smem_u32(s_bias);
       for (int b = 0; b < p.B; ++b) {
         for (int j = 0; j < n_tiles; ++j) {
           const int u = unit++;
@@ -553,23 +554,25 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_chain_kernel(const __grid_
           tc_fence_after();
           ++zc[grp];
           const uint32_t taddr = tmem_base + s1 * HC_NT + (static_cast<uint32_t>(quarter * 32) << 16);
-          uint8_t* zt = sA2 + grp * HC_A2_BYTES + m * 128;
+          const uint32_t zt_u = smem_u32(sA2) + grp * HC_A2_BYTES + m * 128;
           for (int g = 0; g < (nt_w >> 5); ++g) {
             uint32_t acc[32];
             tmem_ld32(taddr + g * 32, acc);
             tmem_ld_wait();
-            const float* bb = s_bias + n0 + g * 32;
+            const uint32_t bb_u = bias_u + (n0 + g * 32) * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
+              const float4 b0 = lds_v4f(bb_u + q * 32), b1 = lds_v4f(bb_u + q * 32 + 16);
+              const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
               uint32_t o[4];
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 const int c = q * 8 + 2 * jj;
-                o[jj] = hd_pack_half2(fmaxf(__uint_as_float(acc[c]) + bb[c], 0.0f),
-                                      fmaxf(__uint_as_float(acc[c + 1]) + bb[c + 1], 0.0f));
+                o[jj] = hd_pack_half2(fmaxf(__uint_as_float(acc[c]) + bv[2 * jj], 0.0f),
+                                      fmaxf(__uint_as_float(acc[c + 1]) + bv[2 * jj + 1], 0.0f));
               }
               const int chunk = ((g & 1) * 4 + q) ^ (m & 7);
-              *reinterpret_cast<uint4*>(zt + (g >> 1) * HD_A_BYTES + (chunk << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              sts_v4(zt_u + (g >> 1) * HD_A_BYTES + (chunk << 4), make_uint4(o[0], o[1], o[2], o[3]));
             }
           }
           tc_fence_before();

@@ -304,9 +304,21 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       uint4 rnext[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) rnext[q] = make_uint4(0, 0, 0, 0);
-      if (rrow) {
+      // N <= 96: the whole residual row of this pixel goes in flight before the accumulator is waited for (a group-ahead
+      // prefetch hides a few hundred cycles of an HBM latency of well over a thousand)
+      const bool pre_all = p.rows <= 96;
+      uint4 rall[12];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rnext[q] = ldg_nc_v4(rrow + q * 8);
+      for (int q = 0; q < 12; ++q) rall[q] = make_uint4(0, 0, 0, 0);
+      if (rrow) {
+        if (pre_all) {
+#pragma unroll
+          for (int q = 0; q < 12; ++q)
+            if (q * 8 < p.rows) rall[q] = ldg_nc_v4(rrow + q * 8);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rnext[q] = ldg_nc_v4(rrow + q * 8);
+        }
       }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -317,7 +329,10 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint4 rq[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) { rq[q] = rnext[q]; rnext[q] = make_uint4(0, 0, 0, 0); }
-        if (rrow && g + 1 < real_groups) {
+        if (pre_all) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rq[q] = g == 0 ? rall[q] : (g == 1 ? rall[4 + q] : rall[8 + q]);
+        } else if (rrow && g + 1 < real_groups) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) rnext[q] = ldg_nc_v4(rrow + (g + 1) * 32 + q * 8);
         }
@@ -358,7 +373,8 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // a trailing 16-channel group (Cout = 48: N = 48)
         const int c0 = real_groups * 32;
         uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
-        if (rrow) { r0 = ldg_nc_v4(rrow + c0); r1 = ldg_nc_v4(rrow + c0 + 8); }
+        if (pre_all) { r0 = real_groups == 1 ? rall[4] : rall[8]; r1 = real_groups == 1 ? rall[5] : rall[9]; }
+        else if (rrow) { r0 = ldg_nc_v4(rrow + c0); r1 = ldg_nc_v4(rrow + c0 + 8); }
         uint32_t acc[16];
         tmem_ld16(taddr + c0, acc);
         tmem_ld_wait();

@@ -159,7 +159,7 @@ constexpr int FC_THREADS = 256;
 constexpr int FC_TY = 8, FC_TX = 16;
 
 template <int LANES>
-__global__ void __launch_bounds__(FC_THREADS) fuse_combine_kernel(const CombineParams p) {
+__global__ void __launch_bounds__(FC_THREADS, 4) fuse_combine_kernel(const CombineParams p) {
   const int b = blockIdx.z;
   const int y_base = blockIdx.y * FC_TY, x_base = blockIdx.x * FC_TX;
   const int lanes = p.C8r / LANES;                // threads per pixel (the pad lanes are not worth threads: they would sit

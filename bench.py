@@ -358,7 +358,7 @@ def run_b200(args, rank, world, local_rank):
     stem_gflop = 2.0 * 3 * 64 * 9 * ((nh + 1) // 2) * ((nw + 1) // 2) / 1e9 * len(nets)   # conv1 runs on CUDA cores (stem_conv)
     conv_tflop = (gflop_frame - stem_gflop) * B / 1e3
     achieved = conv_tflop / (conv_ms / 1e3) if conv_ms > 0 else 0.0
-    roof = {"kernel": "tcgen05 implicit-GEMM convs (basicblock_kernel + conv3x3_halo_kernel + conv_tc_kernel + head_chain_kernel / head_fused_kernel, all "
+    roof = {"kernel": "tcgen05 implicit-GEMM convs (basicblock_kernel + conv3x3_pair_kernel + conv3x3_halo_kernel + conv_tc_kernel + head_chain_kernel / head_fused_kernel, all "
                       "launches of one step)", "bound": "tensor",
             "achieved": achieved, "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
             "frac": achieved / pk["tensor_sustained"], "peak_source": pk["source"] + " (sustained fp16/bf16 dense)",

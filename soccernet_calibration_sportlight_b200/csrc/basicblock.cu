@@ -75,7 +75,7 @@ __device__ __forceinline__ uint32_t bb_pack_half2(float a, float b) {
 // step's [G1 | G0] accumulator - and both epilogues share it: it must not idle while an epilogue does arithmetic).
 // `loaded()` runs once the last load has landed, `block(cb, v)` gets v = G0[p] + G1[p + 1] (+ G2[p + 2]).
 template <int NB, bool TAP3, typename FL, typename FB>
-__device__ __forceinline__ void bb_acc_blocks(uint32_t taddr, int ablate, FL&& loaded, FB&& block) {
+__device__ __forceinline__ void bb_acc_blocks(uint32_t taddr, int ablate, FL&& loaded, FB&& block, long long* ldw = nullptr) {
   const bool no_ld = (ablate & 32) != 0;
   constexpr int G = TAP3 ? 3 : 2;
   uint32_t g[2][G][16];
@@ -93,7 +93,9 @@ __device__ __forceinline__ void bb_acc_blocks(uint32_t taddr, int ablate, FL&& l
   }
 #pragma unroll
   for (int cb = 0; cb < NB; ++cb) {
-    if (!no_ld) tmem_ld_wait();
+    if (!no_ld) {
+      if (ldw) { const long long t0_ = clock64(); tmem_ld_wait(); *ldw += clock64() - t0_; } else tmem_ld_wait();
+    }
     if (cb + 1 < NB) {
       if (!no_ld) {
 #pragma unroll
@@ -266,6 +268,7 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
     const int quarter = warp & 3;
     const int m = quarter * 32 + lane;               // pixel of the chunk: row = quarter, column = lane
     const uint32_t sMid_u = smem_u32(sMid), bias_u = smem_u32(s_bias);
+    long long phc[5] = {0, 0, 0, 0, 0};      // profiling: cycles in tcgen05.wait::ld, fence+midEmpty wait, loads+math+stores, fence.proxy.async, arrive
     int slot = 0, as = 0;
     uint32_t ph = 0, aph = 0;
     for (int s = blockIdx.x; s < p.strips; s += gridDim.x) {
@@ -276,11 +279,13 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
         const int my = 4 * j - 1 + quarter;
         const bool inside = col_in && my >= 0 && my < p.H;     // outside the image the intermediate is conv2's zero padding
         BB_WAIT(&t1full[as], aph, 0);
+        const long long s0 = p.dbg ? clock64() : 0;
         tc_fence_after();
         constexpr int ACC = TAP3 ? BB_ACC3 : BB_ACC;
         const uint32_t taddr = tmem_base + as * ACC + (static_cast<uint32_t>(quarter * 32) << 16);
         // the chunk's slot must have been read for the last time (conv2 three steps back)
         BB_WAIT(&midEmpty[slot], ph ^ 1, 1);
+        const long long s1 = p.dbg ? clock64() : 0;
         const uint32_t row = sMid_u + slot * BB_CH + m * 128;
         const uint32_t mrow = sMid_u + BB_SLOTS * BB_CH + m * 128;
         const bool mirror = slot == 0 && m < BB_MIR_ROWS;
@@ -311,15 +316,20 @@ basicblock_kernel(const __grid_constant__ CUtensorMap tmX4, const __grid_constan
             sts_v4(mrow + (((2 * cb) ^ (m & 7)) << 4), lo);
             sts_v4(mrow + (((2 * cb + 1) ^ (m & 7)) << 4), hi);
           }
-        });
+        }, p.dbg ? &phc[0] : nullptr);
+        const long long s2 = p.dbg ? clock64() : 0;
         fence_proxy_async();                          // chunk -> visible to the tensor core's shared-memory reads
+        const long long s3 = p.dbg ? clock64() : 0;
         __syncwarp();
         if (lane == 0) mbar_arrive(&midFull[slot]);
+        if (p.dbg) { const long long s4 = clock64(); phc[1] += s1 - s0; phc[2] += s2 - s1; phc[3] += s3 - s2; phc[4] += s4 - s3; }
         if (++slot == BB_SLOTS) { slot = 0; ph ^= 1; }
         as ^= 1;
         if (as == 0) aph ^= 1;
       }
     }
+    if (p.dbg && warp == 4 && lane == 0)
+      for (int i = 0; i < 5; ++i) p.dbg[148 * 15 + blockIdx.x * 5 + i] = phc[i];
   } else if (warp >= 8) {
     // ---------------------------------------------------------------- epilogue of conv2: + bias + block input, ReLU, store
     const int quarter = warp & 3;
